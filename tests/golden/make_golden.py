@@ -1,0 +1,211 @@
+#!/usr/bin/env python3
+"""Regenerate tests/golden/*.json(.gz) from the reference checkout.
+
+Runs only in the build container (needs /root/reference); the outputs are committed because the
+GPU box has no reference checkout.  Nothing here computes an expected value: every hash below is
+copied from the reference's own tests / fixtures.
+
+Sources (relative to /root/reference):
+  keccak_kat.json      ethash/test/unittests/test_keccak.cpp:20-195   (text + per-length Keccak-256)
+  mptize_kat.json      src/mpt/mpt.zig:326-385                          (7 roots; transcribed below)
+  evmone_mpt_kat.json  evmone/test/unittests/state_mpt_test.cpp:20-333, state_mpt_hash_test.cpp:19-66
+  fixture_states.json.gz
+                       src/tests/fixtures/**.json: `pre` vs genesisBlockHeader.stateRoot, `postState` vs the
+                       last valid block's blockHeader.stateRoot, and per valid block the raw transaction /
+                       withdrawal encodings (decoded from blocks[].rlp) vs transactionsTrie / withdrawalsRoot.
+"""
+import glob
+import gzip
+import hashlib
+import json
+import os
+import re
+import sys
+
+REF = os.environ.get("PHANT_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def dump(name, obj):
+    path = os.path.join(OUT, name)
+    data = json.dumps(obj, separators=(",", ":"), sort_keys=True).encode()
+    if name.endswith(".gz"):
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(data)
+    else:
+        with open(path, "wb") as f:
+            f.write(data + b"\n")
+    print(f"{name}: {os.path.getsize(path)} bytes")
+
+
+# ---------------------------------------------------------------- keccak
+def keccak_kat():
+    src = open(f"{REF}/ethash/test/unittests/test_keccak.cpp").read()
+    m = re.search(r"test_text\s*=\s*((?:\s*\"[^\"]*\")+);", src)
+    text = "".join(re.findall(r"\"([^\"]*)\"", m.group(1)))
+    cases = [(int(n), h) for n, h in re.findall(r"\{\s*(\d+),\s*\"([0-9a-f]{64})\",\s*\"[0-9a-f]{128}\"\}", src)]
+    assert len(cases) > 150 and cases[0][0] == 0
+    dump("keccak_kat.json", {"source": "ethash/test/unittests/test_keccak.cpp:20-195", "text": text,
+                             "cases": [{"len": n, "keccak256": h} for n, h in cases]})
+
+
+# ---------------------------------------------------------------- mptize (src/mpt/mpt.zig:326-385)
+def mptize_kat():
+    H = lambda s: s.encode().hex()
+    cases = [
+        {"name": "empty", "kv": [], "root": "56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"},
+        {"name": "single key - root is a leaf node", "kv": [["01020304", H("hello")]],
+         "root": "6764f7ad0efcbc11b84fe7567773aa4b12bd6b4d35c05bbc3951b58dedb6c8e8"},
+        {"name": "two keys - branch with two embedded leaves", "kv": [["01020304", H("hello1")], ["ff020304", H("hello2")]],
+         "root": "5c474c00e417f587322ae674c948f04e2c217f95bd1dac806af14fa46f8fa403"},
+        {"name": "three keys - two embedded leaves and one hashed",
+         "kv": [["10020304", H("hello1")], ["20020304", H("hello2")], ["30020304", H("hello333333333333333333333333333")]],
+         "root": "86d4d51eedae1cd8ffdfeef48e5f1cd021d84c8d3df0088dfad39e72b37fc4b1"},
+        {"name": "two keys - extension of 3 nibbles and two leaves", "kv": [["00f10304", H("hello1")], ["00f20304", H("hello2")]],
+         "root": "312b81f16960a816e84679c5b9de49471b07b5c11ef0eff19779b083e418f83b"},
+        {"name": "complex - 5 levels, 3 branches, 2 extensions, 4 leaves",
+         "kv": [["345781", H("hello1")], ["345783", H("hello2")], ["345f0203", H("hello3")], ["ff010203", H("hello4")]],
+         "root": "c66c75a03f2b52dfc32b5e229bb2ff7e1d53dcb2b54fe83a1b39418788e0fc66"},
+        {"name": "complex - branch with a value, 40-byte value",
+         "kv": [["34", H("hello1")], ["345781", H("hello2")], ["345783", H("hello3")], ["345f0203", H("hello4")],
+                ["ef010203", H("0123456789012345678901234567890123456789")], ["ff010203", H("hello5")]],
+         "root": "88a4fc29676ebee58aafcd377acd46af6d29044f9bb8220c50ca8dcfe5153fb3"},
+    ]
+    # guard the transcription against the source
+    src = open(f"{REF}/src/mpt/mpt.zig").read()
+    for c in cases:
+        assert c["root"] in src, c["name"]
+    dump("mptize_kat.json", {"source": "src/mpt/mpt.zig:326-385", "cases": cases})
+
+
+# ---------------------------------------------------------------- evmone MPT
+def evmone_kat():
+    src = open(f"{REF}/evmone/test/unittests/state_mpt_test.cpp").read()
+    body = src[src.index("const std::vector<KVH> tests[]"):src.index("// clang-format on", src.index("const std::vector<KVH> tests[]"))]
+    groups = []
+    for g in re.findall(r"\{\s*(?://[^\n]*\n)?((?:\s*\{\"[0-9a-f]+\",\s*\"[^\"]+\",\s*\"[0-9a-f]{64}\"\},?\s*)+)\}", body):
+        groups.append([{"key": k, "value": v.encode().hex(), "root_after_insert": h}
+                       for k, v, h in re.findall(r"\{\"([0-9a-f]+)\",\s*\"([^\"]+)\",\s*\"([0-9a-f]{64})\"\}", g)])
+    assert len(groups) == 26, len(groups)
+    v1, v2 = b"v___________________________1".hex(), b"v___________________________2".hex()
+    examples = [
+        {"name": "leaf_node_example1", "kv": [["010203", b"hello".hex()]],
+         "root": "82c8fd36022fbc91bd6b51580cfd941d3d9994017d59ab2e8293ae9c94c3ab6e"},
+        {"name": "branch_node_example1", "kv": [["41", v1], ["5a", v2]],
+         "root": "1aaa6f712413b9a115730852323deb5f5d796c29151a60a1f55f41a25354cd26"},
+        {"name": "extension_node_example1", "kv": [["585841", v1], ["58585a", v2]],
+         "root": "3eefc183db443d44810b7d925684eb07256e691d5c9cb13215660107121454f9"},
+        {"name": "extension_node_example2", "kv": [[b"XXA".hex(), v1], [b"XYZ".hex(), v2]],
+         "root": "ac28c08fa3ff1d0d2cc9a6423abb7af3f4dcc37aa2210727e7d3009a9b4a34e8"},
+    ]
+    for e in examples:
+        assert e["root"] in src, e["name"]
+    hsrc = open(f"{REF}/evmone/test/unittests/state_mpt_hash_test.cpp").read()
+    zero32 = "00" * 32
+    def acct(addr, nonce=0, balance=0, code="", storage=None):
+        return {"address": addr, "nonce": nonce, "balance": "%064x" % balance, "code": code, "storage": storage or {}}
+    states = [
+        {"name": "empty", "accounts": [], "root": "56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"},
+        {"name": "single_account_v1", "accounts": [acct("00" * 19 + "02", balance=1)],
+         "root": "084f337237951e425716a04fb0aaa74111eda9d9c61767f2497697d0a201c92e"},
+        {"name": "two_accounts_step1", "accounts": [acct("00" * 20)],
+         "root": "0ce23f3c809de377b008a4a3ee94a0834aac8bec1f86e28ffe4fdb5a15b0c785"},
+        {"name": "two_accounts_step2",
+         "accounts": [acct("00" * 20),
+                      acct("00" * 19 + "01", nonce=1, balance=(1 << 256) - 2, code="00",
+                           storage={"00" * 31 + "01": "00" * 31 + "fe", "00" * 31 + "02": "00" * 31 + "fd"})],
+         "root": "d3e845156fca75de99712281581304fbde104c0fc5a102b09288c07cdde0b666"},
+        {"name": "deleted_storage",
+         "accounts": [acct("00" * 19 + "07", storage={"00" * 31 + "01": zero32, "00" * 31 + "02": "00" * 31 + "fd",
+                                                      "00" * 31 + "03": zero32})],
+         "root": "4e7338c16731491e0fb5d1623f5265c17699c970c816bab71d4d717f6071414d"},
+    ]
+    for s in states:
+        assert s["root"] in hsrc or s["name"] == "empty", s["name"]
+    dump("evmone_mpt_kat.json", {"source": "evmone/test/unittests/state_mpt_test.cpp:20-333, state_mpt_hash_test.cpp:19-66",
+                                 "topologies": groups, "examples": examples, "states": states})
+
+
+# ---------------------------------------------------------------- fixtures
+def rlp_decode(b, pos=0):
+    """-> (item, next_pos); item is bytes or list.  For list items also keep the raw encoding."""
+    x = b[pos]
+    if x < 0x80:
+        return b[pos:pos + 1], pos + 1
+    if x < 0xb8:
+        n = x - 0x80
+        return b[pos + 1:pos + 1 + n], pos + 1 + n
+    if x < 0xc0:
+        ll = x - 0xb7
+        n = int.from_bytes(b[pos + 1:pos + 1 + ll], "big")
+        return b[pos + 1 + ll:pos + 1 + ll + n], pos + 1 + ll + n
+    if x < 0xf8:
+        n, start = x - 0xc0, pos + 1
+    else:
+        ll = x - 0xf7
+        n, start = int.from_bytes(b[pos + 1:pos + 1 + ll], "big"), pos + 1 + ll
+    items, p = [], start
+    while p < start + n:
+        q0 = p
+        it, p = rlp_decode(b, p)
+        items.append((it, b[q0:p]))
+    return items, start + n
+
+
+def list_values(block_rlp):
+    """raw trie values of the block's transactions and withdrawals (src/blockchain/blockchain.zig:209-235:
+    value = item.encode(): a legacy tx / withdrawal is its RLP list, a typed tx is the opaque byte string)."""
+    top, _ = rlp_decode(block_rlp)
+    txs_item, wd_item = top[1][0], top[3][0]
+    txs = []
+    for it, raw in txs_item:
+        txs.append(raw if isinstance(it, list) else it)
+    wds = [raw for _, raw in wd_item]
+    return txs, wds
+
+
+def norm_accounts(d):
+    out = []
+    for addr, a in sorted(d.items()):
+        out.append({"address": addr[2:].lower(), "nonce": int(a["nonce"], 16), "balance": "%064x" % int(a["balance"], 16),
+                    "code": a["code"][2:], "storage": {"%064x" % int(k, 16): "%064x" % int(v, 16) for k, v in a["storage"].items()}})
+    return out
+
+
+def fixtures():
+    tests = []
+    pool = {}      # dedupe identical account tables (most tests share `pre`)
+
+    def intern(accts):
+        blob = json.dumps(accts, sort_keys=True)
+        key = hashlib.sha1(blob.encode()).hexdigest()[:16]
+        pool.setdefault(key, accts)
+        return key
+
+    n_blocks = 0
+    for path in sorted(glob.glob(f"{REF}/src/tests/fixtures/**/*.json", recursive=True)):
+        rel = os.path.relpath(path, f"{REF}/src/tests/fixtures")
+        for name, t in json.load(open(path)).items():
+            valid = [b for b in t["blocks"] if "blockHeader" in b]
+            post_root = (valid[-1]["blockHeader"] if valid else t["genesisBlockHeader"])["stateRoot"][2:]
+            blocks = []
+            for b in valid:
+                txs, wds = list_values(bytes.fromhex(b["rlp"][2:]))
+                blocks.append({"tx_values": [x.hex() for x in txs], "wd_values": [x.hex() for x in wds],
+                               "transactionsTrie": b["blockHeader"]["transactionsTrie"][2:],
+                               "withdrawalsRoot": b["blockHeader"]["withdrawalsRoot"][2:]})
+                n_blocks += 1
+            tests.append({"file": rel, "name": name, "pre": intern(norm_accounts(t["pre"])),
+                          "pre_root": t["genesisBlockHeader"]["stateRoot"][2:],
+                          "post": intern(norm_accounts(t["postState"])), "post_root": post_root, "blocks": blocks})
+    print(f"fixtures: {len(tests)} tests, {n_blocks} valid blocks, {len(pool)} distinct account tables")
+    dump("fixture_states.json.gz", {"source": "src/tests/fixtures/**", "tables": pool, "tests": tests})
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit(f"{REF} not present: golden files can only be regenerated in the build container")
+    keccak_kat()
+    mptize_kat()
+    evmone_kat()
+    fixtures()

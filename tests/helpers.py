@@ -1,0 +1,157 @@
+"""Shared host-side helpers for the tests (pure Python, no oracle, no GPU)."""
+
+
+def rlp_uint(i):
+    """RLP of an unsigned integer (the key of an index trie, src/blockchain/blockchain.zig:214-232)."""
+    if i == 0:
+        return b"\x80"
+    b = i.to_bytes((i.bit_length() + 7) // 8, "big")
+    return b if len(b) == 1 and b[0] < 0x80 else bytes([0x80 + len(b)]) + b
+
+
+def index_trie_items(values):
+    """(key, value) list of an index trie, sorted the way mptize wants it."""
+    return sorted(((rlp_uint(i), v) for i, v in enumerate(values)), key=lambda kv: kv[0])
+
+
+# ---- a third, independent statement of the proof walk (small cases only) ----
+def _rlp_item(b, pos, end):
+    """strict decode; returns (is_list, payload_start, payload_end, item_end) or None"""
+    if pos >= end:
+        return None
+    x = b[pos]
+    if x < 0x80:
+        return (False, pos, pos + 1, pos + 1)
+    is_list = x >= 0xc0
+    base_s, base_l = (0xc0, 0xf7) if is_list else (0x80, 0xb7)
+    if x <= base_l:
+        n = x - base_s
+        if pos + 1 + n > end:
+            return None
+        if not is_list and n == 1 and b[pos + 1] < 0x80:
+            return None
+        return (is_list, pos + 1, pos + 1 + n, pos + 1 + n)
+    ll = x - base_l
+    if ll > 4 or pos + 1 + ll > end or b[pos + 1] == 0:
+        return None
+    n = int.from_bytes(b[pos + 1:pos + 1 + ll], "big")
+    if n <= 55 or pos + 1 + ll + n > end:
+        return None
+    return (is_list, pos + 1 + ll, pos + 1 + ll + n, pos + 1 + ll + n)
+
+
+EMPTY_ROOT = bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421")
+
+
+def py_verify(keccak, nodes, key32, root):
+    """-> (status, value bytes or None); status 0 reject / 1 present / 2 absent.  See oracle/verify.c R1-R4."""
+    if not nodes:
+        return (2, None) if root == EMPTY_ROOT else (0, None)
+    nib = [n for byte in key32 for n in (byte >> 4, byte & 15)]
+    pos, i, expect = 0, 0, root
+    cur, embedded = None, False
+    while True:
+        if not embedded:
+            if i == len(nodes):
+                return (0, None)
+            cur = nodes[i]
+            if keccak(cur) != expect:
+                return (0, None)
+            i += 1
+        top = _rlp_item(cur, 0, len(cur))
+        if top is None or not top[0] or top[3] != len(cur):
+            return (0, None)
+        items, p = [], top[1]
+        while p < top[2]:
+            it = _rlp_item(cur, p, top[2])
+            if it is None or len(items) == 17:
+                return (0, None)
+            items.append((it, p))
+            p = it[3]
+        if len(items) not in (2, 17):
+            return (0, None)
+        last = i == len(nodes)
+        if len(items) == 17:
+            if pos == 64:
+                it = items[16][0]
+                if it[0] or not last:
+                    return (0, None)
+                return (2, None) if it[1] == it[2] else (1, cur[it[1]:it[2]])
+            child = items[nib[pos]]
+            pos += 1
+        else:
+            it = items[0][0]
+            if it[0] or it[1] == it[2]:
+                return (0, None)
+            hp = cur[it[1]:it[2]]
+            flag = hp[0] >> 4
+            if flag > 3 or (not flag & 1 and hp[0] & 15):
+                return (0, None)
+            path = ([hp[0] & 15] if flag & 1 else []) + [n for byte in hp[1:] for n in (byte >> 4, byte & 15)]
+            if len(path) > 64:
+                return (0, None)
+            match = nib[pos:pos + len(path)] == path
+            if flag & 2:
+                v = items[1][0]
+                if v[0] or not last:
+                    return (0, None)
+                if match and pos + len(path) == 64:
+                    return (1, cur[v[1]:v[2]])
+                return (2, None)
+            if not path:
+                return (0, None)
+            if not match:
+                return (2, None) if last else (0, None)
+            pos += len(path)
+            child = items[1]
+        it, start = child
+        if it[0]:
+            if it[3] - start >= 32:
+                return (0, None)
+            cur, embedded = cur[start:it[3]], True
+            continue
+        embedded = False
+        n = it[2] - it[1]
+        if n == 0:
+            if len(items) == 2:
+                return (0, None)
+            return (2, None) if last else (0, None)
+        if n != 32:
+            return (0, None)
+        expect = cur[it[1]:it[2]]
+
+
+# ---- plain RLP encode (host-side test data preparation) ----
+def rlp_str(b):
+    if len(b) == 1 and b[0] < 0x80:
+        return bytes(b)
+    if len(b) <= 55:
+        return bytes([0x80 + len(b)]) + bytes(b)
+    ll = (len(b).bit_length() + 7) // 8
+    return bytes([0xb7 + ll]) + len(b).to_bytes(ll, "big") + bytes(b)
+
+
+def rlp_list(encoded_items):
+    body = b"".join(encoded_items)
+    if len(body) <= 55:
+        return bytes([0xc0 + len(body)]) + body
+    ll = (len(body).bit_length() + 7) // 8
+    return bytes([0xf7 + ll]) + len(body).to_bytes(ll, "big") + body
+
+
+def rlp_int_be(b):
+    return rlp_str(bytes(b).lstrip(b"\x00"))
+
+
+def secure_account_items(keccak, mptize, accounts):
+    """(keccak(addr), rlp(account)) sorted -- the state trie's key/values
+    (evmone/test/state/mpt_hash.cpp:15-36)."""
+    items = []
+    for a in accounts:
+        st = sorted((keccak(bytes.fromhex(k)), rlp_int_be(bytes.fromhex(v)))
+                    for k, v in a["storage"].items() if int(v, 16) != 0)
+        sroot = mptize(st)
+        body = [rlp_int_be(a["nonce"].to_bytes(8, "big")), rlp_int_be(bytes.fromhex(a["balance"])), rlp_str(sroot),
+                rlp_str(keccak(bytes.fromhex(a["code"])))]
+        items.append((keccak(bytes.fromhex(a["address"])), rlp_list(body)))
+    return sorted(items)

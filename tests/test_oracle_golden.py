@@ -1,0 +1,124 @@
+"""Pin the CPU oracle against every known answer the reference holds for this path.
+
+CPU-only.  If these fail nothing else in the suite means anything: the GPU parity tests compare against
+this oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from helpers import index_trie_items
+
+
+def test_keccak_reference_table(oracle, golden):
+    """ethash/test/unittests/test_keccak.cpp:25-195 -- every prefix length of test_text."""
+    g = golden("keccak_kat.json")
+    text = g["text"].encode()
+    assert len(g["cases"]) >= 160
+    for c in g["cases"]:
+        assert oracle.keccak256(text[:c["len"]]).hex() == c["keccak256"], c["len"]
+
+
+def test_keccak_unaligned(oracle, golden):
+    """ethash/test/unittests/test_keccak.cpp:221-240 -- same table at byte offsets 1..7."""
+    g = golden("keccak_kat.json")
+    text = g["text"].encode()
+    for shift in range(1, 8):
+        buf = np.zeros(len(text) + 16, np.uint8)
+        buf[shift:shift + len(text)] = np.frombuffer(text, np.uint8)
+        off = np.array([shift, shift + 0], np.uint64)
+        for c in g["cases"][::7]:
+            off[1] = shift + c["len"]
+            assert oracle.keccak256_batch(buf, off)[0].tobytes().hex() == c["keccak256"]
+
+
+def test_keccak_constants(oracle):
+    """keccak('') = src/blockchain/vm.zig:22, keccak(0x80) = src/mpt/mpt.zig:10, keccak(0xc0) = src/types/block.zig:13."""
+    assert oracle.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert oracle.keccak256(b"\x80").hex() == "56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"
+    assert oracle.keccak256(b"\xc0").hex() == "1dcc4de8dec75d7aab85b567b6ccd41ad312451b948a7413f0a142fd40d49347"
+
+
+@pytest.mark.skipif(not os.path.exists(oracle_lib.REF_KECCAK_PATH), reason="oracle/_ref not built (no reference checkout)")
+def test_port_equals_compiled_reference_keccak(oracle):
+    """The port vs the reference's keccak.c compiled unchanged (oracle/_ref), random lengths 0..1200."""
+    rng = np.random.default_rng(1)
+    for n in list(range(0, 300)) + [407, 408, 409, 543, 544, 545, 1087, 1088, 1089, 1200]:
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert oracle.keccak256(m) == oracle.ref_keccak256(m), n
+
+
+def test_mptize_reference_roots(oracle, golden):
+    """src/mpt/mpt.zig:326-385 -- the seven `mptize` roots."""
+    for c in golden("mptize_kat.json")["cases"]:
+        kv = [(bytes.fromhex(k), bytes.fromhex(v)) for k, v in c["kv"]]
+        assert oracle.mptize(kv).hex() == c["root"], c["name"]
+
+
+def test_mptize_rejects_unsorted(oracle):
+    with pytest.raises(ValueError):
+        oracle.mptize([(b"\x02", b"a"), (b"\x01", b"b")])
+    with pytest.raises(ValueError):
+        oracle.mptize([(b"\x01", b"a"), (b"\x01", b"b")])
+
+
+def test_evmone_topologies(oracle, golden):
+    """evmone/test/unittests/state_mpt_test.cpp:157-333 -- root after each insertion, all >= 32-byte nodes."""
+    g = golden("evmone_mpt_kat.json")
+    for grp in g["topologies"]:
+        for upto in range(1, len(grp) + 1):
+            kv = sorted((bytes.fromhex(e["key"]), bytes.fromhex(e["value"])) for e in grp[:upto])
+            assert oracle.mptize(kv).hex() == grp[upto - 1]["root_after_insert"]
+    for e in g["examples"]:
+        kv = sorted((bytes.fromhex(k), bytes.fromhex(v)) for k, v in e["kv"])
+        assert oracle.mptize(kv).hex() == e["root"], e["name"]
+
+
+def test_evmone_state_roots(oracle, golden):
+    """evmone/test/unittests/state_mpt_hash_test.cpp:19-66 (go-ethereum derived)."""
+    for s in golden("evmone_mpt_kat.json")["states"]:
+        assert oracle.state_root(s["accounts"]).hex() == s["root"], s["name"]
+
+
+def test_fixture_state_roots(oracle, golden):
+    """84 + 84 state roots: root(pre) == genesis stateRoot, root(postState) == last valid block's stateRoot."""
+    g = golden("fixture_states.json.gz")
+    roots = {k: oracle.state_root(v).hex() for k, v in g["tables"].items()}
+    assert len(g["tests"]) == 84
+    for t in g["tests"]:
+        assert roots[t["pre"]] == t["pre_root"], (t["file"], t["name"], "pre")
+        assert roots[t["post"]] == t["post_root"], (t["file"], t["name"], "post")
+
+
+def test_fixture_list_roots(oracle, golden):
+    """87 + 87 index-trie roots (src/blockchain/blockchain.zig:209-235 key order) vs the block headers."""
+    g = golden("fixture_states.json.gz")
+    n = 0
+    for t in g["tests"]:
+        for b in t["blocks"]:
+            txs = [bytes.fromhex(x) for x in b["tx_values"]]
+            wds = [bytes.fromhex(x) for x in b["wd_values"]]
+            assert oracle.mptize(index_trie_items(txs)).hex() == b["transactionsTrie"]
+            assert oracle.mptize(index_trie_items(wds)).hex() == b["withdrawalsRoot"]
+            n += 1
+    assert n == 87
+
+
+@pytest.mark.skipif(not os.path.exists(oracle_lib.REF_EVMONE_PATH), reason="oracle/_ref not built (no reference checkout)")
+def test_secure_trie_equals_compiled_evmone(oracle):
+    """Random secure tries: mptize restatement vs the reference's vendored evmone MPT compiled unchanged."""
+    import ctypes as C
+    ref = C.CDLL(oracle_lib.REF_EVMONE_PATH)
+    rng = np.random.default_rng(7)
+    for n in (1, 2, 3, 17, 100, 1000):
+        keys = sorted(rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(n))
+        vals = [rng.integers(0, 256, int(rng.integers(33, 120)), dtype=np.uint8).tobytes() for _ in range(n)]
+        k, koff = oracle_lib.csr(keys, np.uint32)
+        v, voff = oracle_lib.csr(vals, np.uint64)
+        out = np.zeros(32, np.uint8)
+        ref.ref_evmone_mpt_root(k.ctypes.data_as(oracle_lib.u8p), koff.ctypes.data_as(oracle_lib.u32p),
+                                v.ctypes.data_as(oracle_lib.u8p), voff.ctypes.data_as(oracle_lib.u64p), C.c_uint64(n),
+                                out.ctypes.data_as(oracle_lib.u8p))
+        assert oracle.mptize(list(zip(keys, vals))) == out.tobytes(), n
