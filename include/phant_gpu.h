@@ -1,0 +1,158 @@
+/* phant_gpu.h -- C ABI of libphantgpu.so: phant's trie/hash hot path on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  phant has no plugin interface for this path -- `mptize`
+ * and `keccak256` are ordinary Zig functions -- so each entry point below names the reference
+ * function or hook it stands behind.  Style follows the one C plugin ABI phant already links, EVMC
+ * (evmone/evmc/include/evmc/evmc.h:1068-1126: version probe, create/destroy, plain structs).
+ * INTEGRATION.md shows the Zig `@cImport` binding and the build.zig lines a maintainer adds.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary, every size explicit, caller owns every buffer;
+ *   - return 0 = OK, negative = error (phant_gpu_strerror).  Accept / reject of a proof is DATA,
+ *     never an error code;
+ *   - pointers are HOST pointers and the library copies host<->device, unless the context was
+ *     switched to device pointers with PHANT_GPU_FLAG_DEVICE_PTRS (benchmarks, callers that already
+ *     hold witnesses in HBM).  Device-pointer inputs must be 16-byte aligned and the byte buffers
+ *     (msgs / nodes) must be readable for 16 bytes past their last offset;
+ *   - a context owns one device, one stream and its scratch memory; it is not re-entrant: one
+ *     context per host thread, or lock around it (phant calls runBlock from httpz worker threads,
+ *     src/main.zig:143-149);
+ *   - there is NO CPU fallback inside the library: without a usable CUDA device create() fails with
+ *     PHANT_GPU_E_NO_DEVICE and the Zig caller keeps its own CPU path.
+ */
+#ifndef PHANT_GPU_H
+#define PHANT_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHANT_GPU_ABI_VERSION 1
+
+enum {
+    PHANT_GPU_OK = 0,
+    PHANT_GPU_E_INVALID = -1,   /* bad argument (null pointer, unsorted keys, offsets not monotone ...) */
+    PHANT_GPU_E_NO_DEVICE = -2, /* no CUDA device / driver */
+    PHANT_GPU_E_OOM = -3,       /* device or pinned-host allocation failed */
+    PHANT_GPU_E_CUDA = -4,      /* any other CUDA runtime error (phant_gpu_last_error has the text) */
+    PHANT_GPU_E_COMM = -5,      /* collective failed (multi-GPU host layer) */
+    PHANT_GPU_E_MALFORMED = -6  /* malformed RLP in a *builder* input (never used for proofs) */
+};
+
+enum {
+    PHANT_GPU_FLAG_DEVICE_PTRS = 1u << 0, /* all data pointers are device pointers; no copies */
+    /* Keccak kernel choice (default = staged thread-per-sponge).  See DESIGN.md "Keccak kernels". */
+    PHANT_GPU_FLAG_KECCAK_DIRECT = 1u << 4, /* thread-per-sponge, direct global loads */
+    PHANT_GPU_FLAG_KECCAK_WARP = 1u << 5,   /* one warp per sponge (north-star layout; slower) */
+    PHANT_GPU_FLAG_NO_BINNING = 1u << 6     /* do not regroup messages by absorb-block count */
+};
+
+typedef struct phant_gpu_ctx phant_gpu_ctx;
+
+typedef struct {
+    int32_t device;      /* CUDA device ordinal */
+    uint32_t flags;      /* PHANT_GPU_FLAG_* */
+    uint64_t reserved[4];
+} phant_gpu_config;
+
+int phant_gpu_abi_version(void);
+int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg);
+void phant_gpu_destroy(phant_gpu_ctx* ctx);
+int phant_gpu_set_flags(phant_gpu_ctx* ctx, uint32_t flags);
+const char* phant_gpu_strerror(int code);
+const char* phant_gpu_last_error(const phant_gpu_ctx* ctx); /* text of the last CUDA error on this context */
+
+/* Per-call counters, reset by the caller: what bench.py reports as gpu_launches / h2d / d2h and the
+ * device time of the dominant kernels (CUDA events on the context's stream). */
+typedef struct {
+    uint64_t launches;      /* kernels launched by this library */
+    uint64_t h2d_bytes, d2h_bytes;
+    double keccak_ms;       /* accumulated device time of the batched Keccak kernels */
+    double walk_ms;         /* accumulated device time of the proof-walk kernel */
+    uint64_t keccak_msgs, keccak_bytes, keccak_perms; /* work the Keccak kernels were given */
+    uint64_t reserved[4];
+} phant_gpu_stats;
+int phant_gpu_get_stats(phant_gpu_ctx* ctx, phant_gpu_stats* out);
+int phant_gpu_reset_stats(phant_gpu_ctx* ctx);
+int phant_gpu_synchronize(phant_gpu_ctx* ctx);
+
+/* K -- batched Keccak-256.  Replaces hasher.keccak256 (src/crypto/hasher.zig:4-8) for many inputs at
+ * once: message i = msgs[off[i] .. off[i+1]) (CSR byte offsets, any alignment, any length incl. 0);
+ * out = n*32 digest bytes.  keccak256WithPrefix (hasher.zig:10-17) is the same call on prefix||data. */
+int phant_gpu_keccak256_batch(phant_gpu_ctx* ctx, const uint8_t* msgs, const uint64_t* off, uint64_t n, uint8_t* out);
+
+/* M -- == mptize (src/mpt/mpt.zig:38-45).  Keys are byte strings sorted lexicographically (a strict
+ * prefix first: KeyVal.lessThan, mpt.zig:31-33), CSR; values CSR.  n == 0 -> empty_mpt_root
+ * (mpt.zig:10).  Unsorted or duplicate keys -> PHANT_GPU_E_INVALID (the reference asserts, mpt.zig:39).
+ * In device-pointer mode only out_root stays a host pointer. */
+int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const uint32_t* key_off, const uint8_t* vals,
+                       const uint64_t* val_off, uint64_t n, uint8_t out_root[32]);
+
+/* S -- state root of a flat account table: the body of the missing StateDB.root()
+ * (hook: src/blockchain/blockchain.zig:83-85; data model src/state/statedb.zig:16-30,
+ * src/state/types.zig:7-33).  Trie contents as in evmone/test/state/mpt_hash.cpp:15-36:
+ * key keccak(addr), value rlp([nonce, balance, storage_root, keccak(code)]); storage key
+ * keccak(slot), value rlp(trim(value)), zero values skipped (statedb.zig:112-119). */
+typedef struct {
+    uint64_t n_accounts;
+    const uint8_t* addr20;      /* n*20 */
+    const uint64_t* nonce;      /* n */
+    const uint8_t* balance32;   /* n*32 big endian */
+    const uint8_t* code;        /* concatenated code bytes */
+    const uint64_t* code_off;   /* n+1 */
+    const uint8_t* slot_keys32; /* total_slots*32 */
+    const uint8_t* slot_vals32; /* total_slots*32 */
+    const uint64_t* slot_off;   /* n+1, in slots */
+} phant_gpu_accounts;
+int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts* accounts, uint8_t out_root[32]);
+
+/* V -- batched Merkle-Patricia proof verification: the body of the TODO at
+ * src/engine_api/execution_payload.zig:177-178.  Proof p = nodes [proof_first[p], proof_first[p+1]),
+ * root first; node j = nodes[node_off[j] .. node_off[j+1]).  n_roots == 1 broadcasts one root.
+ * Outputs (each may be NULL): accept_bitmap ceil(n/64) words, bit p = proof p accepted;
+ * status[p] 0 reject / 1 present / 2 proven absent; val_off/val_len[p] = slice of `nodes` holding
+ * the proven value.  Walk rules: DESIGN.md "Proof walk". */
+typedef struct {
+    uint64_t n_proofs;
+    const uint8_t* nodes;
+    const uint64_t* node_off;    /* n_nodes+1 */
+    const uint64_t* proof_first; /* n_proofs+1 */
+    const uint8_t* keys32;       /* n_proofs*32 */
+    const uint8_t* roots32;      /* n_roots*32 */
+    uint64_t n_roots;
+} phant_gpu_proof_batch;
+int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap,
+                            uint8_t* status, uint64_t* val_off, uint32_t* val_len);
+
+/* U -- resident trie + dirty-frontier root recompute (BASELINE.json "state-root recompute").
+ * Round-1 shape: a complete 16-ary trie with `depth` branch levels (16^depth leaves) whose untouched
+ * leaf hashes come from the synthetic PRNG; update rewrites n_dirty leaves (distinct leaf positions)
+ * and re-hashes only the dirty frontier level by level.  Hook: StateDB.root() after a block. */
+typedef struct phant_gpu_trie phant_gpu_trie;
+typedef struct {
+    uint32_t kind;  /* 0 = complete synthetic trie */
+    uint32_t depth; /* branch levels */
+    uint64_t seed;
+    uint64_t reserved[4];
+} phant_gpu_trie_desc;
+int phant_gpu_trie_open(phant_gpu_ctx* ctx, const phant_gpu_trie_desc* desc, phant_gpu_trie** out);
+int phant_gpu_trie_root(phant_gpu_trie* trie, uint8_t out_root[32]);
+int phant_gpu_trie_update(phant_gpu_trie* trie, const uint8_t* keys32, const uint8_t* leaf_vals,
+                          const uint32_t* val_off, uint64_t n_dirty, uint8_t out_root[32]);
+void phant_gpu_trie_close(phant_gpu_trie* trie);
+
+/* Synthetic witnesses generated on the device (byte-identical to oracle/synth.c).
+ * All pointers are DEVICE pointers regardless of the context flags.  which: 2 = account proofs of
+ * `depth` nodes (config C2), 3 = storage proofs depth 4..12 (config C3; depth ignored).
+ * phant_gpu_synth_sizes fills host totals so the caller can allocate. */
+int phant_gpu_synth_sizes(phant_gpu_ctx* ctx, int which, uint64_t seed, uint64_t first_index, uint64_t n,
+                          uint32_t depth, uint64_t* total_nodes, uint64_t* total_bytes);
+int phant_gpu_synth(phant_gpu_ctx* ctx, int which, uint64_t seed, uint64_t first_index, uint64_t n, uint32_t depth,
+                    int corrupt, uint8_t* nodes, uint64_t* node_off, uint64_t* proof_first, uint8_t* keys32,
+                    uint8_t* roots32);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHANT_GPU_H */

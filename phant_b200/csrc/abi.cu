@@ -1,0 +1,390 @@
+// abi.cu -- the extern "C" surface of libphantgpu.so (include/phant_gpu.h): context, scratch memory,
+// host<->device staging, and the launch sequences behind each entry point.
+#include "../../include/phant_gpu.h"
+#include "common.cuh"
+#include "ctx.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+using namespace phant;
+
+#define CU(expr)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (expr);                                              \
+        if (e_ != cudaSuccess) return ctx->fail(e_, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context plumbing
+// ------------------------------------------------------------------------------------------------
+int phant_gpu_ctx::fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    snprintf(last_error, sizeof last_error, "%s: %s (%s:%d)", cudaGetErrorName(e), what, file, line);
+    cudaGetLastError(); // clear the sticky-less error
+    return e == cudaErrorMemoryAllocation ? PHANT_GPU_E_OOM : PHANT_GPU_E_CUDA;
+}
+
+int DevBuf::reserve(phant_gpu_ctx* ctx, size_t bytes)
+{
+    if (bytes <= cap) return 0;
+    if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256; // a little headroom so repeated calls of similar size do not realloc
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) { want = bytes + 256; e = cudaMalloc(&ptr, want); }
+    if (e != cudaSuccess) { ptr = nullptr; return ctx->fail(e, "cudaMalloc", __FILE__, __LINE__); }
+    cap = want;
+    return 0;
+}
+void DevBuf::release()
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+void phant_gpu_ctx::time_begin(int which)
+{
+    if (n_pairs >= MAX_PAIRS) resolve_times();
+    EventPair& p = pairs[n_pairs];
+    if (!p.a) { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+    p.which = which;
+    cudaEventRecord(p.a, stream);
+}
+void phant_gpu_ctx::time_end()
+{
+    cudaEventRecord(pairs[n_pairs].b, stream);
+    ++n_pairs;
+}
+void phant_gpu_ctx::resolve_times()
+{
+    if (!n_pairs) return;
+    cudaStreamSynchronize(stream);
+    for (int i = 0; i < n_pairs; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pairs[i].a, pairs[i].b) == cudaSuccess) {
+            if (pairs[i].which == 0) stats.keccak_ms += ms; else stats.walk_ms += ms;
+        }
+    }
+    n_pairs = 0;
+}
+
+extern "C" int phant_gpu_abi_version(void) { return PHANT_GPU_ABI_VERSION; }
+
+extern "C" const char* phant_gpu_strerror(int code)
+{
+    switch (code) {
+    case PHANT_GPU_OK: return "ok";
+    case PHANT_GPU_E_INVALID: return "invalid argument";
+    case PHANT_GPU_E_NO_DEVICE: return "no usable CUDA device";
+    case PHANT_GPU_E_OOM: return "out of device memory";
+    case PHANT_GPU_E_CUDA: return "CUDA runtime error";
+    case PHANT_GPU_E_COMM: return "collective communication error";
+    case PHANT_GPU_E_MALFORMED: return "malformed RLP in builder input";
+    default: return "unknown error";
+    }
+}
+
+extern "C" int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg)
+{
+    if (!out) return PHANT_GPU_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return PHANT_GPU_E_NO_DEVICE; }
+    const int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= count) return PHANT_GPU_E_INVALID;
+    if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return PHANT_GPU_E_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return PHANT_GPU_E_NO_DEVICE; }
+    if (prop.major < 10) return PHANT_GPU_E_NO_DEVICE; // sm_100a code only
+    phant_gpu_ctx* ctx = new (std::nothrow) phant_gpu_ctx();
+    if (!ctx) return PHANT_GPU_E_OOM;
+    ctx->device = dev;
+    ctx->flags = cfg ? cfg->flags : 0;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return PHANT_GPU_E_CUDA;
+    }
+    *out = ctx;
+    return PHANT_GPU_OK;
+}
+
+extern "C" void phant_gpu_destroy(phant_gpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : ctx->all_bufs()) b->release();
+    for (int i = 0; i < phant_gpu_ctx::MAX_PAIRS; ++i)
+        if (ctx->pairs[i].a) { cudaEventDestroy(ctx->pairs[i].a); cudaEventDestroy(ctx->pairs[i].b); }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int phant_gpu_set_flags(phant_gpu_ctx* ctx, uint32_t flags)
+{
+    if (!ctx) return PHANT_GPU_E_INVALID;
+    ctx->flags = flags;
+    return PHANT_GPU_OK;
+}
+extern "C" const char* phant_gpu_last_error(const phant_gpu_ctx* ctx) { return ctx ? ctx->last_error : "null context"; }
+
+extern "C" int phant_gpu_synchronize(phant_gpu_ctx* ctx)
+{
+    if (!ctx) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHANT_GPU_OK;
+}
+extern "C" int phant_gpu_get_stats(phant_gpu_ctx* ctx, phant_gpu_stats* out)
+{
+    if (!ctx || !out) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    ctx->resolve_times();
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->perms_pending) {
+        unsigned long long p = 0;
+        CU(cudaMemcpy(&p, ctx->d_perms.ptr, sizeof p, cudaMemcpyDeviceToHost));
+        ctx->stats.keccak_perms += p;
+        CU(cudaMemset(ctx->d_perms.ptr, 0, sizeof p));
+        ctx->perms_pending = false;
+    }
+    *out = ctx->stats;
+    return PHANT_GPU_OK;
+}
+extern "C" int phant_gpu_reset_stats(phant_gpu_ctx* ctx)
+{
+    if (!ctx) return PHANT_GPU_E_INVALID;
+    phant_gpu_stats tmp;
+    int rc = phant_gpu_get_stats(ctx, &tmp);
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K: hash a CSR message set that is already on the device
+// ------------------------------------------------------------------------------------------------
+int phant_gpu_ctx::hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint64_t total_bytes, uint8_t* d_out)
+{
+    phant_gpu_ctx* ctx = this;
+    if (n == 0) return PHANT_GPU_OK;
+    if (n > 0xffffffffull) return PHANT_GPU_E_INVALID; // message indices are 32-bit on the device
+    KeccakVariant variant = KECCAK_STAGED;
+    if (flags & PHANT_GPU_FLAG_KECCAK_DIRECT) variant = KECCAK_DIRECT;
+    if (flags & PHANT_GPU_FLAG_KECCAK_WARP) variant = KECCAK_WARP;
+    if (variant == KECCAK_STAGED && ((uintptr_t)d_msgs & 15)) variant = KECCAK_DIRECT; // bulk copies need 16-byte alignment
+
+    // classify (always: it also counts the permutations for the stats) and, optionally, regroup
+    if (int rc = d_perms.reserve(ctx, 64)) return rc;
+    if (!perms_init) { CU(cudaMemsetAsync(d_perms.ptr, 0, 8, stream)); perms_init = true; }
+    if (int rc = d_cls.reserve(ctx, n)) return rc;
+    if (int rc = d_idx.reserve(ctx, 4 * n)) return rc;
+    CU(launch_keccak_classify(stream, device, d_off, n, (uint8_t*)d_cls.ptr, (uint32_t*)d_idx.ptr, (unsigned long long*)d_perms.ptr));
+    stats.launches++;
+    perms_pending = true;
+    const uint32_t* order = nullptr;
+    const bool regroup = !(flags & PHANT_GPU_FLAG_NO_BINNING) && variant != KECCAK_WARP && n >= 4096;
+    if (regroup) {
+        if (int rc = d_cls2.reserve(ctx, n)) return rc;
+        if (int rc = d_order.reserve(ctx, 4 * n)) return rc;
+        size_t temp = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint8_t*)d_cls.ptr, (uint8_t*)d_cls2.ptr, (const uint32_t*)d_idx.ptr,
+                                           (uint32_t*)d_order.ptr, (int64_t)n, 0, 4, stream));
+        if (int rc = d_cub.reserve(ctx, temp)) return rc;
+        CU(cub::DeviceRadixSort::SortPairs(d_cub.ptr, temp, (const uint8_t*)d_cls.ptr, (uint8_t*)d_cls2.ptr, (const uint32_t*)d_idx.ptr,
+                                           (uint32_t*)d_order.ptr, (int64_t)n, 0, 4, stream));
+        order = (const uint32_t*)d_order.ptr;
+    }
+    time_begin(0);
+    CU(launch_keccak(stream, device, variant, d_msgs, d_off, order, n, d_out));
+    time_end();
+    stats.launches++;
+    stats.keccak_msgs += n;
+    stats.keccak_bytes += total_bytes;
+    return PHANT_GPU_OK;
+}
+
+// offsets must start the CSR at off[0] (any value) and be monotone; returns total bytes via *total
+static int check_offsets_host(const uint64_t* off, uint64_t n, uint64_t* total)
+{
+    for (uint64_t i = 0; i < n; ++i)
+        if (off[i + 1] < off[i]) return PHANT_GPU_E_INVALID;
+    *total = off[n];
+    return PHANT_GPU_OK;
+}
+
+extern "C" int phant_gpu_keccak256_batch(phant_gpu_ctx* ctx, const uint8_t* msgs, const uint64_t* off, uint64_t n, uint8_t* out)
+{
+    if (!ctx || (n && (!off || !out))) return PHANT_GPU_E_INVALID;
+    if (n == 0) return PHANT_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) {
+        uint64_t last = 0;
+        CU(cudaMemcpyAsync(&last, off + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (last && !msgs) return PHANT_GPU_E_INVALID;
+        return ctx->hash_csr(msgs, off, n, last, out);
+    }
+    uint64_t total = 0;
+    if (int rc = check_offsets_host(off, n, &total)) return rc;
+    if (total && !msgs) return PHANT_GPU_E_INVALID;
+    if (int rc = ctx->d_msgs.reserve(ctx, total + 64)) return rc;
+    if (int rc = ctx->d_off.reserve(ctx, 8 * (n + 1))) return rc;
+    if (int rc = ctx->d_out.reserve(ctx, 32 * n)) return rc;
+    if (total) CU(cudaMemcpyAsync(ctx->d_msgs.ptr, msgs, total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_off.ptr, off, 8 * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += total + 8 * (n + 1);
+    if (int rc = ctx->hash_csr((const uint8_t*)ctx->d_msgs.ptr, (const uint64_t*)ctx->d_off.ptr, n, total, (uint8_t*)ctx->d_out.ptr)) return rc;
+    CU(cudaMemcpyAsync(out, ctx->d_out.ptr, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += 32 * n;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHANT_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// V: proof verification
+// ------------------------------------------------------------------------------------------------
+extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap,
+                                       uint8_t* status, uint64_t* val_off, uint32_t* val_len)
+{
+    if (!ctx || !in) return PHANT_GPU_E_INVALID;
+    const uint64_t np = in->n_proofs;
+    if (np == 0) return PHANT_GPU_OK;
+    if (!in->node_off || !in->proof_first || !in->keys32 || !in->roots32) return PHANT_GPU_E_INVALID;
+    if (in->n_roots != 1 && in->n_roots != np) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bm_bytes = ((np + 63) / 64) * 8;
+
+    if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) {
+        uint64_t n_nodes = 0, total = 0;
+        CU(cudaMemcpyAsync(&n_nodes, in->proof_first + np, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (n_nodes) {
+            CU(cudaMemcpyAsync(&total, in->node_off + n_nodes, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
+        if (int rc = ctx->hash_csr(in->nodes, in->node_off, n_nodes, total, (uint8_t*)ctx->d_digests.ptr)) return rc;
+        if (accept_bitmap) CU(cudaMemsetAsync(accept_bitmap, 0, bm_bytes, ctx->stream));
+        ctx->time_begin(1);
+        CU(launch_walk(ctx->stream, ctx->device, np, in->nodes, in->node_off, in->proof_first, in->keys32, in->roots32, in->n_roots,
+                       (const uint8_t*)ctx->d_digests.ptr, accept_bitmap, status, val_off, val_len));
+        ctx->time_end();
+        ctx->stats.launches++;
+        return PHANT_GPU_OK; // asynchronous on the context's stream: phant_gpu_synchronize() to wait
+    }
+
+    // host pointers: validate the CSR arrays, stage everything, run, copy the verdicts back
+    const uint64_t n_nodes = in->proof_first[np];
+    for (uint64_t p = 0; p < np; ++p)
+        if (in->proof_first[p + 1] < in->proof_first[p]) return PHANT_GPU_E_INVALID;
+    uint64_t total = 0;
+    if (int rc = check_offsets_host(in->node_off, n_nodes, &total)) return rc;
+    if (total && !in->nodes) return PHANT_GPU_E_INVALID;
+    if (int rc = ctx->d_msgs.reserve(ctx, total + 64)) return rc;
+    if (int rc = ctx->d_off.reserve(ctx, 8 * (n_nodes + 1))) return rc;
+    if (int rc = ctx->d_first.reserve(ctx, 8 * (np + 1))) return rc;
+    if (int rc = ctx->d_keys.reserve(ctx, 32 * np)) return rc;
+    if (int rc = ctx->d_roots.reserve(ctx, 32 * in->n_roots)) return rc;
+    if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
+    if (int rc = ctx->d_bitmap.reserve(ctx, bm_bytes)) return rc;
+    if (int rc = ctx->d_status.reserve(ctx, np)) return rc;
+    if (val_off) if (int rc = ctx->d_voff.reserve(ctx, 8 * np)) return rc;
+    if (val_len) if (int rc = ctx->d_vlen.reserve(ctx, 4 * np)) return rc;
+    cudaStream_t s = ctx->stream;
+    if (total) CU(cudaMemcpyAsync(ctx->d_msgs.ptr, in->nodes, total, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_off.ptr, in->node_off, 8 * (n_nodes + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_first.ptr, in->proof_first, 8 * (np + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_keys.ptr, in->keys32, 32 * np, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_roots.ptr, in->roots32, 32 * in->n_roots, cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += total + 8 * (n_nodes + 1) + 8 * (np + 1) + 32 * np + 32 * in->n_roots;
+    if (int rc = ctx->hash_csr((const uint8_t*)ctx->d_msgs.ptr, (const uint64_t*)ctx->d_off.ptr, n_nodes, total, (uint8_t*)ctx->d_digests.ptr))
+        return rc;
+    CU(cudaMemsetAsync(ctx->d_bitmap.ptr, 0, bm_bytes, s));
+    ctx->time_begin(1);
+    CU(launch_walk(s, ctx->device, np, (const uint8_t*)ctx->d_msgs.ptr, (const uint64_t*)ctx->d_off.ptr, (const uint64_t*)ctx->d_first.ptr,
+                   (const uint8_t*)ctx->d_keys.ptr, (const uint8_t*)ctx->d_roots.ptr, in->n_roots, (const uint8_t*)ctx->d_digests.ptr,
+                   (uint64_t*)ctx->d_bitmap.ptr, (uint8_t*)ctx->d_status.ptr, val_off ? (uint64_t*)ctx->d_voff.ptr : nullptr,
+                   val_len ? (uint32_t*)ctx->d_vlen.ptr : nullptr));
+    ctx->time_end();
+    ctx->stats.launches++;
+    if (accept_bitmap) { CU(cudaMemcpyAsync(accept_bitmap, ctx->d_bitmap.ptr, bm_bytes, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += bm_bytes; }
+    if (status) { CU(cudaMemcpyAsync(status, ctx->d_status.ptr, np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += np; }
+    if (val_off) { CU(cudaMemcpyAsync(val_off, ctx->d_voff.ptr, 8 * np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += 8 * np; }
+    if (val_len) { CU(cudaMemcpyAsync(val_len, ctx->d_vlen.ptr, 4 * np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += 4 * np; }
+    CU(cudaStreamSynchronize(s));
+    return PHANT_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic witnesses (device pointers)
+// ------------------------------------------------------------------------------------------------
+namespace phant { uint64_t synth_c2_bytes_per_proof(uint32_t depth); }
+
+static int c3_scans(phant_gpu_ctx* ctx, uint64_t seed, uint64_t first_index, uint64_t n)
+{
+    // per-proof node / byte counts, then exclusive scans with a trailing total (n+1 entries)
+    if (int rc = ctx->d_tmp_a.reserve(ctx, 8 * (n + 1))) return rc;
+    if (int rc = ctx->d_tmp_b.reserve(ctx, 8 * (n + 1))) return rc;
+    if (int rc = ctx->d_scan_a.reserve(ctx, 8 * (n + 1))) return rc;
+    if (int rc = ctx->d_scan_b.reserve(ctx, 8 * (n + 1))) return rc;
+    CU(cudaMemsetAsync((uint64_t*)ctx->d_tmp_a.ptr + n, 0, 8, ctx->stream));
+    CU(cudaMemsetAsync((uint64_t*)ctx->d_tmp_b.ptr + n, 0, 8, ctx->stream));
+    CU(launch_synth_c3_sizes(ctx->stream, ctx->device, seed, first_index, n, (uint64_t*)ctx->d_tmp_a.ptr, (uint64_t*)ctx->d_tmp_b.ptr));
+    ctx->stats.launches++;
+    size_t temp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, temp, (const uint64_t*)ctx->d_tmp_a.ptr, (uint64_t*)ctx->d_scan_a.ptr, (int64_t)(n + 1), ctx->stream));
+    if (int rc = ctx->d_cub.reserve(ctx, temp)) return rc;
+    CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.ptr, temp, (const uint64_t*)ctx->d_tmp_a.ptr, (uint64_t*)ctx->d_scan_a.ptr, (int64_t)(n + 1), ctx->stream));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.ptr, temp, (const uint64_t*)ctx->d_tmp_b.ptr, (uint64_t*)ctx->d_scan_b.ptr, (int64_t)(n + 1), ctx->stream));
+    return PHANT_GPU_OK;
+}
+
+extern "C" int phant_gpu_synth_sizes(phant_gpu_ctx* ctx, int which, uint64_t seed, uint64_t first_index, uint64_t n, uint32_t depth,
+                                     uint64_t* total_nodes, uint64_t* total_bytes)
+{
+    if (!ctx || !total_nodes || !total_bytes) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (which == 2) {
+        if (depth < 2 || depth > 64) return PHANT_GPU_E_INVALID;
+        *total_nodes = n * depth;
+        *total_bytes = n * synth_c2_bytes_per_proof(depth);
+        return PHANT_GPU_OK;
+    }
+    if (which != 3) return PHANT_GPU_E_INVALID;
+    *total_nodes = *total_bytes = 0;
+    if (n == 0) return PHANT_GPU_OK;
+    if (int rc = c3_scans(ctx, seed, first_index, n)) return rc;
+    CU(cudaMemcpyAsync(total_nodes, (uint64_t*)ctx->d_scan_a.ptr + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(total_bytes, (uint64_t*)ctx->d_scan_b.ptr + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHANT_GPU_OK;
+}
+
+extern "C" int phant_gpu_synth(phant_gpu_ctx* ctx, int which, uint64_t seed, uint64_t first_index, uint64_t n, uint32_t depth,
+                               int corrupt, uint8_t* nodes, uint64_t* node_off, uint64_t* proof_first, uint8_t* keys32, uint8_t* roots32)
+{
+    if (!ctx || !nodes || !node_off || !proof_first || !keys32 || !roots32) return PHANT_GPU_E_INVALID;
+    if (n == 0) return PHANT_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    if (which == 2) {
+        if (depth < 2 || depth > 64) return PHANT_GPU_E_INVALID;
+        CU(launch_synth_c2(ctx->stream, ctx->device, seed, first_index, n, depth, corrupt, nodes, node_off, proof_first, keys32, roots32));
+        ctx->stats.launches++;
+    } else if (which == 3) {
+        if (int rc = c3_scans(ctx, seed, first_index, n)) return rc;
+        CU(cudaMemcpyAsync(proof_first, ctx->d_scan_a.ptr, 8 * (n + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(launch_synth_c3(ctx->stream, ctx->device, seed, first_index, n, corrupt, (const uint64_t*)ctx->d_scan_a.ptr,
+                           (const uint64_t*)ctx->d_scan_b.ptr, nodes, node_off, keys32, roots32));
+        ctx->stats.launches++;
+    } else {
+        return PHANT_GPU_E_INVALID;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHANT_GPU_OK;
+}

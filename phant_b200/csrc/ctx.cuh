@@ -1,0 +1,55 @@
+// ctx.cuh -- the context object behind `phant_gpu_ctx*` (include/phant_gpu.h).
+#pragma once
+#include "../../include/phant_gpu.h"
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <initializer_list>
+
+struct phant_gpu_ctx;
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int reserve(phant_gpu_ctx* ctx, size_t bytes); // grows (never shrinks); contents are not preserved
+    void release();
+};
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int which = 0; // 0 keccak, 1 walk
+};
+
+struct phant_gpu_ctx {
+    int device = 0;
+    uint32_t flags = 0;
+    cudaStream_t stream = nullptr;
+    char last_error[256] = {0};
+    phant_gpu_stats stats = {};
+
+    // staging + scratch (device)
+    DevBuf d_msgs, d_off, d_out;                                          // K
+    DevBuf d_first, d_keys, d_roots, d_digests, d_bitmap, d_status, d_voff, d_vlen; // V
+    DevBuf d_cls, d_cls2, d_idx, d_order, d_cub, d_perms;                 // regrouping
+    DevBuf d_tmp_a, d_tmp_b, d_scan_a, d_scan_b;                          // synth / builders
+    DevBuf d_b0, d_b1, d_b2, d_b3, d_b4, d_b5, d_b6, d_b7, d_b8, d_b9;    // trie builder scratch
+    bool perms_init = false, perms_pending = false;
+
+    std::initializer_list<DevBuf*> all_bufs()
+    {
+        return {&d_msgs, &d_off, &d_out, &d_first, &d_keys, &d_roots, &d_digests, &d_bitmap, &d_status, &d_voff, &d_vlen,
+                &d_cls, &d_cls2, &d_idx, &d_order, &d_cub, &d_perms, &d_tmp_a, &d_tmp_b, &d_scan_a, &d_scan_b,
+                &d_b0, &d_b1, &d_b2, &d_b3, &d_b4, &d_b5, &d_b6, &d_b7, &d_b8, &d_b9};
+    }
+
+    // device timing of the dominant kernels: event pairs recorded on `stream`, resolved lazily
+    static constexpr int MAX_PAIRS = 64;
+    EventPair pairs[MAX_PAIRS];
+    int n_pairs = 0;
+    void time_begin(int which);
+    void time_end();
+    void resolve_times();
+
+    int fail(cudaError_t e, const char* what, const char* file, int line);
+    int hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint64_t total_bytes, uint8_t* d_out);
+};

@@ -1,0 +1,157 @@
+// keccak_f1600.cuh -- Keccak-f[1600] and the Keccak-256 sponge for one thread (sm_100a).
+//
+// One sponge per THREAD: the 25 64-bit lanes live in 50 registers, every index below is a compile-time
+// constant after unrolling, so there is no local memory and no cross-lane traffic.  Integer work only:
+// theta/chi fold into LOP3 (3-input logic), rho is two funnel shifts (SHF) per lane.  This is the
+// B200 statement of the function phant reaches through src/crypto/hasher.zig:4-8 (Zig std Keccak256);
+// the native twin in the reference tree is ethash/lib/keccak/keccak.c:58-269 (permutation) and
+// :301-354 (sponge).  Round constants are the standard ones (keccak.c:38-46).
+#pragma once
+#include <stdint.h>
+
+namespace phant {
+
+__constant__ uint64_t KECCAK_RC[24] = {
+    0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
+    0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+    0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
+    0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+    0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+    0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+
+constexpr int KECCAK_RATE = 136;       // bytes absorbed per permutation (Keccak-256)
+constexpr int KECCAK_RATE_WORDS = 17;  // 64-bit lanes per block
+
+// 64-bit rotate left by a compile-time amount, as two 32-bit funnel shifts.
+template <int N>
+__device__ __forceinline__ uint64_t rol64(uint64_t x)
+{
+    if constexpr (N == 0) return x;
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    uint32_t rlo, rhi;
+    if constexpr (N == 32) {
+        rlo = hi; rhi = lo;
+    } else if constexpr (N < 32) {
+        rlo = __funnelshift_l(hi, lo, N);
+        rhi = __funnelshift_l(lo, hi, N);
+    } else {
+        rlo = __funnelshift_l(lo, hi, N - 32);
+        rhi = __funnelshift_l(hi, lo, N - 32);
+    }
+    return ((uint64_t)rhi << 32) | rlo;
+}
+
+// theta + rho + pi for one input lane: B[pi(I)] = rol(A[I] ^ D[I % 5], RHO[I])
+#define PHANT_RHOPI(I, J, R) b[J] = rol64<R>(a[I] ^ d[(I) % 5]);
+
+__device__ __forceinline__ void keccak_round(uint64_t (&a)[25], uint64_t rc)
+{
+    uint64_t c[5], d[5], b[25];
+#pragma unroll
+    for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+    d[0] = c[4] ^ rol64<1>(c[1]);
+    d[1] = c[0] ^ rol64<1>(c[2]);
+    d[2] = c[1] ^ rol64<1>(c[3]);
+    d[3] = c[2] ^ rol64<1>(c[4]);
+    d[4] = c[3] ^ rol64<1>(c[0]);
+    // lane I=x+5y moves to J=y+5((2x+3y)%5) rotated by RHO[I]
+    PHANT_RHOPI(0, 0, 0)    PHANT_RHOPI(1, 10, 1)   PHANT_RHOPI(2, 20, 62)  PHANT_RHOPI(3, 5, 28)   PHANT_RHOPI(4, 15, 27)
+    PHANT_RHOPI(5, 16, 36)  PHANT_RHOPI(6, 1, 44)   PHANT_RHOPI(7, 11, 6)   PHANT_RHOPI(8, 21, 55)  PHANT_RHOPI(9, 6, 20)
+    PHANT_RHOPI(10, 7, 3)   PHANT_RHOPI(11, 17, 10) PHANT_RHOPI(12, 2, 43)  PHANT_RHOPI(13, 12, 25) PHANT_RHOPI(14, 22, 39)
+    PHANT_RHOPI(15, 23, 41) PHANT_RHOPI(16, 8, 45)  PHANT_RHOPI(17, 18, 15) PHANT_RHOPI(18, 3, 21)  PHANT_RHOPI(19, 13, 8)
+    PHANT_RHOPI(20, 14, 18) PHANT_RHOPI(21, 24, 2)  PHANT_RHOPI(22, 9, 61)  PHANT_RHOPI(23, 19, 56) PHANT_RHOPI(24, 4, 14)
+#pragma unroll
+    for (int y = 0; y < 25; y += 5) {
+#pragma unroll
+        for (int x = 0; x < 5; ++x) a[y + x] = b[y + x] ^ (~b[y + (x + 1) % 5] & b[y + (x + 2) % 5]);
+    }
+    a[0] ^= rc;
+}
+#undef PHANT_RHOPI
+
+// UNROLL rounds per loop trip (24 % UNROLL == 0).  2 keeps the body inside the instruction cache.
+template <int UNROLL = 2>
+__device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25])
+{
+#pragma unroll 1
+    for (int r = 0; r < 24; r += UNROLL) {
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) keccak_round(a, KECCAK_RC[r + k]);
+    }
+}
+
+// ---- byte-granular message access ------------------------------------------------------------
+// A message starts at any byte address.  `w` points at the 8-byte aligned word holding its first
+// byte and `sh` = 8 * (address & 7): message word k is the funnel of aligned words k and k+1.
+struct MsgView {
+    const uint64_t* w;
+    uint32_t sh; // 0, 8, .. 56
+};
+__device__ __forceinline__ MsgView msg_view(const void* p)
+{
+    const uintptr_t a = (uintptr_t)p;
+    return MsgView{(const uint64_t*)(a & ~(uintptr_t)7), (uint32_t)(a & 7) * 8};
+}
+__device__ __forceinline__ uint64_t funnel64(uint64_t lo, uint64_t hi, uint32_t sh)
+{
+    return sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+}
+
+// Absorb one full 136-byte block starting at message word `base`.
+template <int UNROLL>
+__device__ __forceinline__ void absorb_full(uint64_t (&st)[25], const MsgView& v, uint32_t base)
+{
+    uint64_t w[KECCAK_RATE_WORDS + 1];
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_WORDS; ++k) w[k] = v.w[base + k];
+    // with a misaligned start the byte after the block is still a message byte of this block's
+    // last word, so word base+17 always holds valid bytes when sh != 0
+    w[KECCAK_RATE_WORDS] = v.sh ? v.w[base + KECCAK_RATE_WORDS] : 0;
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_WORDS; ++k) st[k] ^= funnel64(w[k], w[k + 1], v.sh);
+    keccak_f1600<UNROLL>(st);
+}
+
+// Absorb the last (partial, possibly empty) block: `rem` < 136 bytes at message word `base`, then
+// pad 0x01 .. 0x80 (keccak.c:341-347) and permute.  Never touches a word holding no message byte.
+template <int UNROLL>
+__device__ __forceinline__ void absorb_final(uint64_t (&st)[25], const MsgView& v, uint32_t base, uint32_t rem)
+{
+    const uint32_t mis = v.sh >> 3;
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_WORDS; ++k) {
+        const int valid = (int)rem - 8 * k; // message bytes in this word (may be <= 0 or >= 8)
+        uint64_t word = 0;
+        if (valid > 0) {
+            const uint64_t lo = v.w[base + k];
+            const uint64_t hi = (mis + (valid > 8 ? 8 : valid) > 8) ? v.w[base + k + 1] : 0;
+            word = funnel64(lo, hi, v.sh);
+            if (valid < 8) word &= (1ull << (8 * valid)) - 1;
+        }
+        if (valid >= 0 && valid < 8) word ^= 1ull << (8 * valid); // 0x01 right after the message
+        st[k] ^= word;
+    }
+    st[KECCAK_RATE_WORDS - 1] ^= 0x8000000000000000ull;
+    keccak_f1600<UNROLL>(st);
+}
+
+// Whole-message Keccak-256 from global or shared memory (generic pointer), any alignment.
+template <int UNROLL = 2>
+__device__ __forceinline__ void keccak256_thread(const uint8_t* p, uint64_t len, uint64_t (&digest)[4])
+{
+    uint64_t st[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) st[i] = 0;
+    const MsgView v = msg_view(p);
+    uint32_t base = 0;
+    while (len >= KECCAK_RATE) {
+        absorb_full<UNROLL>(st, v, base);
+        base += KECCAK_RATE_WORDS;
+        len -= KECCAK_RATE;
+    }
+    absorb_final<UNROLL>(st, v, base, (uint32_t)len);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) digest[i] = st[i];
+}
+
+} // namespace phant

@@ -1,0 +1,317 @@
+// keccak_kernels.cu -- batched Keccak-256 over CSR messages (entry point K of include/phant_gpu.h).
+//
+// Replaces N calls of hasher.keccak256 (reference src/crypto/hasher.zig:4-8; per-node use in
+// src/mpt/mpt.zig:203-209,241-247,273-280) by one launch.  Three kernels, same results:
+//
+//   staged  (default)  one sponge per thread, state in registers; each lane's message bytes are brought
+//                      from HBM into its private shared-memory slot by the bulk-copy engine
+//                      (cp.async.bulk -> SASS UBLKCP, completion on a per-warp mbarrier), 4 rate blocks
+//                      per trip, and read back as 64-bit words.  No thread ever issues a global load
+//                      for message bytes, so the strided (one-message-per-lane) access pattern never
+//                      reaches the LSU as 32 uncoalesced sectors.
+//   direct             same sponge, message words loaded straight from global memory (fallback when
+//                      the buffer is not 16-byte aligned / padded; also the simplest correct kernel).
+//   warp               the layout BASELINE.json's north star describes: one WARP per sponge, lane i
+//                      holds state lane i (25 of 32 lanes busy), coalesced 136-byte block loads, theta /
+//                      pi / chi as warp shuffles.  Kept for comparison: it issues ~7x more
+//                      instructions per permutation than one-sponge-per-thread.
+//
+// Messages may be regrouped by number of rate blocks (`order`), so that the 32 lanes of a warp run the
+// same number of permutations.
+#include "common.cuh"
+#include "keccak_f1600.cuh"
+
+namespace phant {
+
+// ------------------------------------------------------------------------------------------------
+// direct
+// ------------------------------------------------------------------------------------------------
+template <int UNROLL>
+__global__ void __launch_bounds__(128)
+keccak256_direct_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
+                        const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t m = order ? order[i] : i;
+        const uint64_t beg = off[m], end = off[m + 1];
+        uint64_t dg[4];
+        keccak256_thread<UNROLL>(msgs + beg, end - beg, dg);
+        uint64_t* o = reinterpret_cast<uint64_t*>(out + 32 * m);
+        o[0] = dg[0]; o[1] = dg[1]; o[2] = dg[2]; o[3] = dg[3];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// staged: bulk-copy engine -> per-lane shared-memory slot -> registers
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGE_BLOCKS = 4;                                    // rate blocks per trip
+constexpr int STAGE_SLOT = 560;                                    // 4*136 + 15 rounded to 16; 16*35 (odd)
+constexpr int STAGE_WARPS = 4;
+constexpr int STAGE_SMEM = 128 + STAGE_WARPS * 32 * STAGE_SLOT;    // barriers + slots = 71,808 B -> 3 CTAs/SM
+static_assert(STAGE_SLOT % 16 == 0 && STAGE_SLOT >= STAGE_BLOCKS * KECCAK_RATE + 15, "slot too small");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int UNROLL>
+__global__ void __launch_bounds__(STAGE_WARPS * 32)
+keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
+                        const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar = smem_u32(smem) + 8 * warp;
+    uint8_t* slot = smem + 128 + (warp * 32 + lane) * STAGE_SLOT;
+    const uint32_t slot_s = smem_u32(slot);
+    if (lane == 0) mbar_init(bar, 32);
+    fence_proxy_async();
+    __syncthreads();
+    uint32_t parity = 0;
+
+    const uint64_t n_tiles = (n + 31) / 32;
+    for (uint64_t tile = (uint64_t)blockIdx.x * STAGE_WARPS + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * STAGE_WARPS) {
+        const uint64_t idx = tile * 32 + lane;
+        const bool active = idx < n;
+        uint64_t m = 0, cur = 0, end = 0;
+        if (active) {
+            m = order ? order[idx] : idx;
+            cur = off[m];
+            end = off[m + 1];
+        }
+        uint64_t st[25];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) st[i] = 0;
+        bool done = !active;
+
+        while (!__all_sync(0xffffffffu, done)) {
+            // -- ask the copy engine for this lane's next <= 4 blocks (16-byte aligned window) --
+            const uint64_t need = done ? 0 : end - cur;
+            const uint64_t a0 = cur & ~(uint64_t)15;
+            uint32_t cs = 0;
+            if (need) {
+                const uint64_t span = ((end - a0) + 15) & ~(uint64_t)15;
+                cs = span < STAGE_SLOT ? (uint32_t)span : STAGE_SLOT;
+                fence_proxy_async(); // my earlier reads of the slot are ordered before the engine's writes
+                mbar_arrive_expect_tx(bar, cs);
+                bulk_g2s(slot_s, msgs + a0, cs, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            if (!done) {
+                const uint32_t skew = (uint32_t)(cur - a0);
+                const uint64_t in_slot = cs - skew; // message bytes present in the slot (cs == 0 -> need == 0)
+                const uint64_t avail = need < in_slot ? need : in_slot;
+                const MsgView v = msg_view(slot + skew);
+                const uint32_t nfull = (uint32_t)(avail / KECCAK_RATE);
+                uint32_t base = 0;
+                for (uint32_t b = 0; b < nfull; ++b) {
+                    absorb_full<UNROLL>(st, v, base);
+                    base += KECCAK_RATE_WORDS;
+                }
+                if (avail == need) { // the message ends inside this window: pad and finish
+                    absorb_final<UNROLL>(st, v, base, (uint32_t)(avail - (uint64_t)nfull * KECCAK_RATE));
+                    done = true;
+                } else {
+                    cur += (uint64_t)nfull * KECCAK_RATE;
+                }
+            }
+        }
+        if (active) {
+            uint4* o = reinterpret_cast<uint4*>(out + 32 * m);
+            o[0] = make_uint4((uint32_t)st[0], (uint32_t)(st[0] >> 32), (uint32_t)st[1], (uint32_t)(st[1] >> 32));
+            o[1] = make_uint4((uint32_t)st[2], (uint32_t)(st[2] >> 32), (uint32_t)st[3], (uint32_t)(st[3] >> 32));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp: one sponge per warp (north-star layout)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t rolv64(uint64_t x, uint32_t n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+
+__global__ void __launch_bounds__(256)
+keccak256_warp_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint64_t n,
+                      uint8_t* __restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp_id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    // per-lane constants: lane i = x + 5y holds A[x,y]
+    const uint32_t x = lane % 5, y = (lane % 25) / 5;
+    constexpr uint32_t RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    uint32_t rho = 0;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) if (lane == (uint32_t)i) rho = RHO[i];
+    // pi: destination (X,Y) takes source (x', y') with X = y', Y = 2x'+3y'  =>  x' = (X + 3Y) % 5, y' = X
+    const uint32_t pi_src = ((x + 3 * y) % 5) + 5 * x;
+    const uint32_t col1 = (x + 1) % 5, col4 = (x + 4) % 5;
+    const uint32_t row1 = 5 * y + (x + 1) % 5, row2 = 5 * y + (x + 2) % 5;
+    const uint32_t FULL = 0xffffffffu;
+
+    for (uint64_t m = warp_id; m < n; m += n_warps) {
+        const uint64_t beg = off[m], end = off[m + 1];
+        uint64_t len = end - beg;
+        const MsgView v = msg_view(msgs + beg);
+        uint64_t s = 0; // my state lane (lanes >= 25 carry junk that nobody reads)
+        uint32_t base = 0;
+        bool last = false;
+        while (!last) {
+            // ---- absorb one block: lanes 0..16 take word k = lane ----
+            uint64_t word = 0;
+            if (len >= KECCAK_RATE) {
+                uint64_t lo = 0;
+                if (lane <= KECCAK_RATE_WORDS && (lane < KECCAK_RATE_WORDS || v.sh)) lo = v.w[base + lane];
+                const uint64_t hi = __shfl_down_sync(FULL, lo, 1);
+                word = lane < KECCAK_RATE_WORDS ? funnel64(lo, hi, v.sh) : 0;
+                len -= KECCAK_RATE;
+                base += KECCAK_RATE_WORDS;
+            } else {
+                const uint32_t rem = (uint32_t)len, mis = v.sh >> 3;
+                // aligned words that hold message bytes of this block: [0, ceil((mis+rem)/8))
+                const uint32_t n_al = (mis + rem + 7) / 8;
+                uint64_t lo = (rem && lane < n_al) ? v.w[base + lane] : 0;
+                const uint64_t hi = __shfl_down_sync(FULL, lo, 1);
+                if (lane < KECCAK_RATE_WORDS) {
+                    const int valid = (int)rem - 8 * (int)lane;
+                    if (valid > 0) {
+                        word = funnel64(lo, hi, v.sh);
+                        if (valid < 8) word &= (1ull << (8 * valid)) - 1;
+                    }
+                    if (valid >= 0 && valid < 8) word ^= 1ull << (8 * valid);
+                    if (lane == KECCAK_RATE_WORDS - 1) word ^= 0x8000000000000000ull;
+                }
+                last = true;
+            }
+            s ^= word;
+            // ---- Keccak-f[1600] across the warp ----
+#pragma unroll 1
+            for (int r = 0; r < 24; ++r) {
+                uint64_t c = s;                                        // theta: column parity
+                c ^= __shfl_sync(FULL, s, (lane + 5) % 25);
+                c ^= __shfl_sync(FULL, s, (lane + 10) % 25);
+                c ^= __shfl_sync(FULL, s, (lane + 15) % 25);
+                c ^= __shfl_sync(FULL, s, (lane + 20) % 25);
+                const uint64_t cm = __shfl_sync(FULL, c, col4), cp = __shfl_sync(FULL, c, col1);
+                s ^= cm ^ rolv64(cp, 1);
+                s = rolv64(s, rho);                                    // rho
+                s = __shfl_sync(FULL, s, pi_src);                      // pi
+                const uint64_t b1 = __shfl_sync(FULL, s, row1), b2 = __shfl_sync(FULL, s, row2);
+                s ^= ~b1 & b2;                                         // chi
+                if (lane == 0) s ^= KECCAK_RC[r];                      // iota
+            }
+        }
+        if (lane < 4) reinterpret_cast<uint64_t*>(out + 32 * m)[lane] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// regrouping by permutation count
+// ------------------------------------------------------------------------------------------------
+__global__ void keccak_class_kernel(const uint64_t* __restrict__ off, uint64_t n, uint8_t* __restrict__ cls,
+                                    uint32_t* __restrict__ idx, unsigned long long* __restrict__ perms)
+{
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t nb = (off[i + 1] - off[i]) / KECCAK_RATE + 1; // permutations of this message
+        cls[i] = (uint8_t)(15 - (nb > 16 ? 15 : nb - 1));            // heavy classes first
+        idx[i] = (uint32_t)i;
+        local += nb;
+    }
+    // one atomic per warp
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(perms, local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int keccak_num_sms(int device)
+{
+    static int cached[64] = {0};
+    if (device < 0 || device >= 64) device = 0;
+    if (!cached[device]) cudaDeviceGetAttribute(&cached[device], cudaDevAttrMultiProcessorCount, device);
+    return cached[device] ? cached[device] : 148;
+}
+
+cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, const uint8_t* msgs, const uint64_t* off,
+                          const uint32_t* order, uint64_t n, uint8_t* out)
+{
+    if (n == 0) return cudaSuccess;
+    const int sms = keccak_num_sms(device);
+    switch (variant) {
+    case KECCAK_STAGED: {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(keccak256_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_SMEM);
+            if (e != cudaSuccess) return e;
+            cudaFuncSetAttribute(keccak256_staged_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            attr_set = true;
+        }
+        const uint64_t tiles = (n + 31) / 32;
+        uint64_t blocks = (tiles + STAGE_WARPS - 1) / STAGE_WARPS;
+        const uint64_t cap = (uint64_t)sms * 3; // 3 CTAs of 71.8 KB fit one SM
+        if (blocks > cap) blocks = cap;
+        keccak256_staged_kernel<2><<<(unsigned)blocks, STAGE_WARPS * 32, STAGE_SMEM, s>>>(msgs, off, order, n, out);
+        break;
+    }
+    case KECCAK_DIRECT: {
+        uint64_t blocks = (n + 127) / 128;
+        const uint64_t cap = (uint64_t)sms * 8;
+        if (blocks > cap) blocks = cap;
+        keccak256_direct_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(msgs, off, order, n, out);
+        break;
+    }
+    case KECCAK_WARP: {
+        uint64_t blocks = (n + 7) / 8;
+        const uint64_t cap = (uint64_t)sms * 8;
+        if (blocks > cap) blocks = cap;
+        keccak256_warp_kernel<<<(unsigned)blocks, 256, 0, s>>>(msgs, off, n, out);
+        break;
+    }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* off, uint64_t n, uint8_t* cls, uint32_t* idx,
+                                   unsigned long long* perms)
+{
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + 255) / 256;
+    const uint64_t cap = (uint64_t)keccak_num_sms(device) * 8;
+    if (blocks > cap) blocks = cap;
+    keccak_class_kernel<<<(unsigned)blocks, 256, 0, s>>>(off, n, cls, idx, perms);
+    return cudaGetLastError();
+}
+
+} // namespace phant

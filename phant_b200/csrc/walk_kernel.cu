@@ -1,0 +1,226 @@
+// walk_kernel.cu -- Merkle-Patricia proof walk (entry point V of include/phant_gpu.h).
+//
+// Fills the hook phant leaves open at src/engine_api/execution_payload.zig:177-178.  Every node of the
+// batch has already been hashed by the batched Keccak kernel; this kernel walks each proof's chain:
+// strict RLP decode of the branch / extension / leaf encodings that src/mpt/mpt.zig:170-281 produces,
+// the child reference for the key's next nibble compared with the next node's digest (or followed in
+// place when the child is embedded, mpt.zig:104,112), until a terminal decides present / absent.
+// Rules R1-R4 are written out in DESIGN.md ("Proof walk"); oracle/verify.c is the CPU statement the
+// tests hold this against.  One proof per thread: chains are short (<= ~12 nodes), independent, and
+// the node bytes were just streamed through L2 by the hash kernel.
+#include "common.cuh"
+
+namespace phant {
+namespace {
+
+enum { ST_REJECT = 0, ST_PRESENT = 1, ST_ABSENT = 2 };
+
+struct Item {
+    uint32_t is_list;
+    uint32_t pay_off; // from the item's first byte
+    uint32_t pay_len;
+};
+
+// Strict decode of one RLP item at p (avail bytes).  Returns its total size, 0 if malformed.
+__device__ __forceinline__ uint32_t rlp_item(const uint8_t* p, uint32_t avail, Item& it)
+{
+    if (avail == 0) return 0;
+    const uint32_t b = p[0];
+    if (b < 0x80) { it.is_list = 0; it.pay_off = 0; it.pay_len = 1; return 1; }
+    const uint32_t is_list = b >= 0xc0;
+    const uint32_t base_short = is_list ? 0xc0 : 0x80, base_long = is_list ? 0xf7 : 0xb7;
+    it.is_list = is_list;
+    if (b <= base_long) {
+        const uint32_t len = b - base_short;
+        if (1 + len > avail) return 0;
+        if (!is_list && len == 1 && p[1] < 0x80) return 0; // single byte must encode as itself
+        it.pay_off = 1; it.pay_len = len;
+        return 1 + len;
+    }
+    const uint32_t n = b - base_long;
+    if (n > 4 || 1 + n > avail) return 0;
+    if (p[1] == 0) return 0;
+    uint64_t len = 0;
+    for (uint32_t i = 0; i < n; ++i) len = (len << 8) | p[1 + i];
+    if (len <= 55) return 0;
+    if (1 + n + len > avail) return 0;
+    it.pay_off = 1 + n; it.pay_len = (uint32_t)len;
+    return (uint32_t)(1 + n + len);
+}
+
+__device__ __forceinline__ bool eq32(const uint8_t* a, const uint32_t (&e)[8])
+{
+    // a may be unaligned (a hash inside a node)
+    uint32_t diff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t w = (uint32_t)a[4 * i] | ((uint32_t)a[4 * i + 1] << 8) | ((uint32_t)a[4 * i + 2] << 16) | ((uint32_t)a[4 * i + 3] << 24);
+        diff |= w ^ e[i];
+    }
+    return diff == 0;
+}
+__device__ __forceinline__ void load32(const uint8_t* a, uint32_t (&e)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        e[i] = (uint32_t)a[4 * i] | ((uint32_t)a[4 * i + 1] << 8) | ((uint32_t)a[4 * i + 2] << 16) | ((uint32_t)a[4 * i + 3] << 24);
+}
+
+__constant__ uint8_t EMPTY_ROOT[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45,
+                                       0xe6, 0x92, 0xc0, 0xf8, 0x6e, 0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c,
+                                       0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+
+__device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off, uint64_t first,
+                        uint64_t last, const uint8_t* __restrict__ key, const uint8_t* __restrict__ root,
+                        const uint8_t* __restrict__ digests, uint64_t& voff, uint32_t& vlen)
+{
+    voff = 0; vlen = 0;
+    uint32_t expect[8];
+    load32(root, expect);
+    if (first == last) return eq32(EMPTY_ROOT, expect) ? ST_ABSENT : ST_REJECT;
+
+    uint32_t pos = 0; // nibbles of the key consumed
+    uint64_t i = first;
+    const uint8_t* cur = nullptr;
+    uint32_t cur_len = 0;
+    bool embedded = false;
+
+    for (;;) {
+        if (!embedded) {
+            if (i == last) return ST_REJECT; // R3: a hash reference needs a node
+            const uint64_t o = node_off[i];
+            const uint64_t l = node_off[i + 1] - o;
+            if (l > 0xffffffffull) return ST_REJECT;
+            cur = nodes + o;
+            cur_len = (uint32_t)l;
+            if (!eq32(digests + 32 * i, expect)) return ST_REJECT; // R1
+            ++i;
+        }
+        Item top;
+        const uint32_t tot = rlp_item(cur, cur_len, top);
+        if (tot == 0 || !top.is_list || tot != cur_len) return ST_REJECT; // R2
+        const uint8_t* pay = cur + top.pay_off;
+        const uint32_t pl = top.pay_len;
+
+        // one pass over the items: remember item 0, item 1, the item at the key's nibble and item 16
+        const uint32_t want = pos < 64 ? ((pos & 1) ? (key[pos >> 1] & 15u) : (key[pos >> 1] >> 4)) : 16u;
+        Item it0{}, it1{}, itw{}, it16{};
+        uint32_t off0 = 0, off1 = 0, offw = 0, off16 = 0;
+        uint32_t cnt = 0, o = 0;
+        while (o < pl) {
+            if (cnt == 17) return ST_REJECT;
+            Item it;
+            const uint32_t t = rlp_item(pay + o, pl - o, it);
+            if (t == 0) return ST_REJECT;
+            if (cnt == 0) { it0 = it; off0 = o; }
+            if (cnt == 1) { it1 = it; off1 = o; }
+            if (cnt == want) { itw = it; offw = o; }
+            if (cnt == 16) { it16 = it; off16 = o; }
+            o += t;
+            ++cnt;
+        }
+        if (cnt != 17 && cnt != 2) return ST_REJECT;
+
+        Item child;
+        uint32_t child_off;
+        if (cnt == 17) {
+            if (pos == 64) { // key exhausted: the branch value decides
+                if (it16.is_list || i != last) return ST_REJECT;
+                if (it16.pay_len == 0) return ST_ABSENT;
+                voff = (uint64_t)(pay + off16 + it16.pay_off - nodes);
+                vlen = it16.pay_len;
+                return ST_PRESENT;
+            }
+            child = itw; child_off = offw;
+            ++pos;
+        } else {
+            if (it0.is_list || it0.pay_len == 0) return ST_REJECT;
+            const uint8_t* hp = pay + off0 + it0.pay_off;
+            const uint32_t flag = hp[0] >> 4;
+            if (flag > 3) return ST_REJECT;
+            if (!(flag & 1) && (hp[0] & 15)) return ST_REJECT;
+            const uint32_t plen = 2 * (it0.pay_len - 1) + (flag & 1);
+            if (plen > 64) return ST_REJECT;
+            bool match = 64 - pos >= plen;
+            if (match) {
+                // path nibble j: odd flag -> nibble 0 is hp[0]&15, then bytes; even -> bytes from hp[1]
+                for (uint32_t j = 0; j < plen; ++j) {
+                    const uint32_t q = j + 2 - (flag & 1); // nibble index inside hp (2 nibbles per byte)
+                    const uint32_t pn = (q & 1) ? (hp[q >> 1] & 15u) : (hp[q >> 1] >> 4);
+                    const uint32_t kq = pos + j;
+                    const uint32_t kn = (kq & 1) ? (key[kq >> 1] & 15u) : (key[kq >> 1] >> 4);
+                    if (pn != kn) { match = false; break; }
+                }
+            }
+            if (flag & 2) { // leaf
+                if (it1.is_list || i != last) return ST_REJECT;
+                if (match && pos + plen == 64) {
+                    voff = (uint64_t)(pay + off1 + it1.pay_off - nodes);
+                    vlen = it1.pay_len;
+                    return ST_PRESENT;
+                }
+                return ST_ABSENT;
+            }
+            if (plen == 0) return ST_REJECT;
+            if (!match) return i == last ? ST_ABSENT : ST_REJECT;
+            pos += plen;
+            child = it1; child_off = off1;
+        }
+        if (child.is_list) { // embedded child (< 32 bytes), walked in place
+            const uint32_t tot_child = child.pay_off + child.pay_len;
+            if (tot_child >= 32) return ST_REJECT;
+            cur = pay + child_off;
+            cur_len = tot_child;
+            embedded = true;
+            continue;
+        }
+        embedded = false;
+        if (child.pay_len == 0) {
+            if (cnt == 2) return ST_REJECT;
+            return i == last ? ST_ABSENT : ST_REJECT;
+        }
+        if (child.pay_len != 32) return ST_REJECT;
+        load32(pay + child_off + child.pay_off, expect);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
+            const uint64_t* __restrict__ proof_first, const uint8_t* __restrict__ keys32,
+            const uint8_t* __restrict__ roots32, uint64_t n_roots, const uint8_t* __restrict__ digests,
+            uint64_t* __restrict__ bitmap, uint8_t* __restrict__ status, uint64_t* __restrict__ val_off,
+            uint32_t* __restrict__ val_len)
+{
+    const uint64_t n_padded = (n_proofs + 31) & ~(uint64_t)31; // whole warps, so the ballot is complete
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_padded; p += (uint64_t)gridDim.x * blockDim.x) {
+        int st = ST_REJECT;
+        if (p < n_proofs) {
+            uint64_t vo;
+            uint32_t vl;
+            st = walk_one(nodes, node_off, proof_first[p], proof_first[p + 1], keys32 + 32 * p,
+                          roots32 + (n_roots == 1 ? 0 : 32 * p), digests, vo, vl);
+            if (status) status[p] = (uint8_t)st;
+            if (val_off) val_off[p] = vo;
+            if (val_len) val_len[p] = vl;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, st != ST_REJECT);
+        if (bitmap && (threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(bitmap)[p >> 5] = word;
+    }
+}
+
+} // namespace
+
+cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,
+                        const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
+                        const uint8_t* digests, uint64_t* bitmap, uint8_t* status, uint64_t* val_off, uint32_t* val_len)
+{
+    if (n_proofs == 0) return cudaSuccess;
+    uint64_t blocks = (n_proofs + 127) / 128;
+    const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
+    if (blocks > cap) blocks = cap;
+    walk_kernel<<<(unsigned)blocks, 128, 0, s>>>(n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, digests,
+                                                 bitmap, status, val_off, val_len);
+    return cudaGetLastError();
+}
+
+} // namespace phant

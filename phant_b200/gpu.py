@@ -1,0 +1,220 @@
+"""ctypes binding of include/phant_gpu.h (libphantgpu.so).  Fails loudly when the library is missing."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libphantgpu.so")
+
+FLAG_DEVICE_PTRS = 1 << 0
+FLAG_KECCAK_DIRECT = 1 << 4
+FLAG_KECCAK_WARP = 1 << 5
+FLAG_NO_BINNING = 1 << 6
+
+u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+
+
+class PhantGpuError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__(f"{where}: {_lib().phant_gpu_strerror(code).decode()} ({code}) {detail}")
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint64 * 4)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("keccak_ms", C.c_double),
+                ("walk_ms", C.c_double), ("keccak_msgs", C.c_uint64), ("keccak_bytes", C.c_uint64), ("keccak_perms", C.c_uint64),
+                ("reserved", C.c_uint64 * 4)]
+
+
+class Accounts(C.Structure):
+    _fields_ = [("n_accounts", C.c_uint64), ("addr20", C.c_void_p), ("nonce", C.c_void_p), ("balance32", C.c_void_p),
+                ("code", C.c_void_p), ("code_off", C.c_void_p), ("slot_keys32", C.c_void_p), ("slot_vals32", C.c_void_p),
+                ("slot_off", C.c_void_p)]
+
+
+class ProofBatch(C.Structure):
+    _fields_ = [("n_proofs", C.c_uint64), ("nodes", C.c_void_p), ("node_off", C.c_void_p), ("proof_first", C.c_void_p),
+                ("keys32", C.c_void_p), ("roots32", C.c_void_p), ("n_roots", C.c_uint64)]
+
+
+class TrieDesc(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("depth", C.c_uint32), ("seed", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+
+
+EXPORTS = [
+    "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_strerror",
+    "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
+    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_state_root", "phant_gpu_verify_proofs",
+    "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
+    "phant_gpu_synth_sizes", "phant_gpu_synth",
+]
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.phant_gpu_abi_version.restype = C.c_int
+    L.phant_gpu_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.phant_gpu_destroy.argtypes = [vp]
+    L.phant_gpu_destroy.restype = None
+    L.phant_gpu_set_flags.argtypes = [vp, C.c_uint32]
+    L.phant_gpu_strerror.argtypes = [C.c_int]
+    L.phant_gpu_strerror.restype = C.c_char_p
+    L.phant_gpu_last_error.argtypes = [vp]
+    L.phant_gpu_last_error.restype = C.c_char_p
+    L.phant_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.phant_gpu_reset_stats.argtypes = [vp]
+    L.phant_gpu_synchronize.argtypes = [vp]
+    L.phant_gpu_keccak256_batch.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    L.phant_gpu_mpt_root.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp]
+    L.phant_gpu_state_root.argtypes = [vp, C.POINTER(Accounts), vp]
+    L.phant_gpu_verify_proofs.argtypes = [vp, C.POINTER(ProofBatch), vp, vp, vp, vp]
+    L.phant_gpu_trie_open.argtypes = [vp, C.POINTER(TrieDesc), C.POINTER(vp)]
+    L.phant_gpu_trie_root.argtypes = [vp, vp]
+    L.phant_gpu_trie_update.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
+    L.phant_gpu_trie_close.argtypes = [vp]
+    L.phant_gpu_trie_close.restype = None
+    L.phant_gpu_synth_sizes.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u64p, u64p]
+    L.phant_gpu_synth.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, vp, vp, vp, vp, vp]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    """numpy array / torch tensor / int / None -> raw address"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+class Context:
+    """One device, one stream (phant_gpu_ctx).  Not thread safe."""
+
+    def __init__(self, device=0, flags=0):
+        self._h = C.c_void_p()
+        cfg = Config(device, flags)
+        rc = _lib().phant_gpu_create(C.byref(self._h), C.byref(cfg))
+        if rc != 0:
+            self._h = None
+            raise PhantGpuError(rc, "phant_gpu_create")
+        self.device = device
+        self.flags = flags
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().phant_gpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _chk(self, rc, where):
+        if rc != 0:
+            raise PhantGpuError(rc, where, _lib().phant_gpu_last_error(self._h).decode())
+
+    def set_flags(self, flags):
+        self._chk(_lib().phant_gpu_set_flags(self._h, flags), "set_flags")
+        self.flags = flags
+
+    def synchronize(self):
+        self._chk(_lib().phant_gpu_synchronize(self._h), "synchronize")
+
+    def stats(self):
+        s = Stats()
+        self._chk(_lib().phant_gpu_get_stats(self._h, C.byref(s)), "get_stats")
+        return {k: getattr(s, k) for k, _ in Stats._fields_ if k != "reserved"}
+
+    def reset_stats(self):
+        self._chk(_lib().phant_gpu_reset_stats(self._h), "reset_stats")
+
+    # K
+    def keccak256_batch(self, msgs, off, n, out):
+        self._chk(_lib().phant_gpu_keccak256_batch(self._h, _ptr(msgs), _ptr(off), n, _ptr(out)), "keccak256_batch")
+
+    # M
+    def mpt_root(self, keys, key_off, vals, val_off, n):
+        out = np.zeros(32, np.uint8)
+        self._chk(_lib().phant_gpu_mpt_root(self._h, _ptr(keys), _ptr(key_off), _ptr(vals), _ptr(val_off), n, _ptr(out)), "mpt_root")
+        return out.tobytes()
+
+    # S
+    def state_root(self, n, addr20, nonce, balance32, code, code_off, slot_keys32, slot_vals32, slot_off):
+        a = Accounts(n, _ptr(addr20), _ptr(nonce), _ptr(balance32), _ptr(code), _ptr(code_off), _ptr(slot_keys32),
+                     _ptr(slot_vals32), _ptr(slot_off))
+        out = np.zeros(32, np.uint8)
+        self._chk(_lib().phant_gpu_state_root(self._h, C.byref(a), _ptr(out)), "state_root")
+        return out.tobytes()
+
+    # V
+    def verify_proofs(self, n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, bitmap=None, status=None,
+                      val_off=None, val_len=None):
+        b = ProofBatch(n_proofs, _ptr(nodes), _ptr(node_off), _ptr(proof_first), _ptr(keys32), _ptr(roots32), n_roots)
+        self._chk(_lib().phant_gpu_verify_proofs(self._h, C.byref(b), _ptr(bitmap), _ptr(status), _ptr(val_off), _ptr(val_len)),
+                  "verify_proofs")
+
+    # U
+    def trie_open(self, depth, seed=0x5048414E54, kind=0):
+        return ResidentTrie(self, depth, seed, kind)
+
+    # synthetic (device pointers)
+    def synth_sizes(self, which, n, depth=8, first=0, seed=0x5048414E54):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._chk(_lib().phant_gpu_synth_sizes(self._h, which, seed, first, n, depth, C.byref(a), C.byref(b)), "synth_sizes")
+        return a.value, b.value
+
+    def synth(self, which, n, nodes, node_off, proof_first, keys32, roots32, depth=8, first=0, corrupt=True, seed=0x5048414E54):
+        self._chk(_lib().phant_gpu_synth(self._h, which, seed, first, n, depth, int(corrupt), _ptr(nodes), _ptr(node_off),
+                                         _ptr(proof_first), _ptr(keys32), _ptr(roots32)), "synth")
+
+
+class ResidentTrie:
+    def __init__(self, ctx, depth, seed, kind):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        d = TrieDesc(kind, depth, seed)
+        ctx._chk(_lib().phant_gpu_trie_open(ctx._h, C.byref(d), C.byref(self._h)), "trie_open")
+
+    def root(self):
+        out = np.zeros(32, np.uint8)
+        self.ctx._chk(_lib().phant_gpu_trie_root(self._h, _ptr(out)), "trie_root")
+        return out.tobytes()
+
+    def update(self, keys32, leaf_vals, val_off, n_dirty):
+        out = np.zeros(32, np.uint8)
+        self.ctx._chk(_lib().phant_gpu_trie_update(self._h, _ptr(keys32), _ptr(leaf_vals), _ptr(val_off), n_dirty, _ptr(out)),
+                      "trie_update")
+        return out.tobytes()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().phant_gpu_trie_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def abi_version():
+    return _lib().phant_gpu_abi_version()
+
+
+def exported_symbols():
+    """every symbol include/phant_gpu.h declares that the loaded library really exports"""
+    L = _lib()
+    return [s for s in EXPORTS if hasattr(L, s)]

@@ -1,0 +1,143 @@
+"""V: proof walk on the GPU vs the oracle (status, accept bitmap, value slice: bit-exact)."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from gpu_util import bit
+from helpers import secure_account_items
+from test_oracle_proofs import batch_of, mutations
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from phant_b200 import gpu
+    c = gpu.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_verify(ctx, nodes, node_off, first, keys, roots, flags=0):
+    n = len(first) - 1
+    bitmap = np.zeros((n + 63) // 64, np.uint64)
+    status = np.full(n, 77, np.uint8)
+    voff = np.zeros(n, np.uint64)
+    vlen = np.zeros(n, np.uint32)
+    ctx.set_flags(flags)
+    ctx.verify_proofs(n, np.ascontiguousarray(nodes), node_off, first, np.ascontiguousarray(keys), np.ascontiguousarray(roots),
+                      roots.size // 32, bitmap, status, voff, vlen)
+    return bitmap, status, voff, vlen
+
+
+def assert_same(ctx, oracle, proofs, flags=0):
+    nodes, node_off, first, keys, roots = batch_of(proofs)
+    want = oracle.verify_proofs(nodes, node_off, first, keys, roots)
+    got = gpu_verify(ctx, nodes, node_off, first, keys, roots, flags)
+    assert (got[1] == want[1]).all(), np.nonzero(got[1] != want[1])[0][:10]
+    assert (got[0] == want[0]).all()
+    present = want[1] == 1
+    assert (got[2][present] == want[2][present]).all() and (got[3][present] == want[3][present]).all()
+    return want[1]
+
+
+@pytest.mark.parametrize("flags", [0, 1 << 4, 1 << 5])
+def test_fixture_proofs_and_mutations(ctx, oracle, golden, flags):
+    g = golden("fixture_states.json.gz")
+    rng = np.random.default_rng(3)
+    proofs = []
+    for tkey, accounts in sorted(g["tables"].items())[:30]:
+        if not accounts:
+            continue
+        items = secure_account_items(oracle.keccak256, oracle.mptize, accounts)
+        trie = oracle.trie(items)
+        root = trie.root()
+        mine = [(trie.prove(k), k, root) for k, _ in items[:50]]
+        for _ in range(4):
+            k = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+            mine.append((trie.prove(k), k, root))
+        proofs += mine
+        for i in rng.choice(len(mine), size=min(4, len(mine)), replace=False):
+            proofs += mutations(*mine[int(i)], rng)
+    st = assert_same(ctx, oracle, proofs, flags)
+    assert {0, 1, 2} <= set(st.tolist())
+
+
+def test_embedded_and_empty(ctx, oracle):
+    base = bytes(range(31))
+    kv = sorted((base + bytes([b]), bytes([v])) for b, v in [(0x10, 1), (0x11, 2), (0x1f, 3), (0x20, 4), (0x77, 5)])
+    trie = oracle.trie(kv)
+    root = trie.root()
+    proofs = [(trie.prove(k), k, root) for k, _ in kv]
+    proofs += [(trie.prove(k), k, root) for k in [base + bytes([0x12]), base + bytes([0x30]), bytes([0xff]) + base]]
+    rng = np.random.default_rng(5)
+    for p in list(proofs[:5]):
+        proofs += mutations(*p, rng)
+    empty = bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421")
+    proofs += [([], bytes(32), empty), ([], bytes(32), bytes(32))]
+    assert_same(ctx, oracle, proofs)
+
+
+def test_single_root_broadcast(ctx, oracle):
+    rng = np.random.default_rng(8)
+    keys = sorted(rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(300))
+    trie = oracle.trie([(k, b"v" * 50) for k in keys])
+    root = trie.root()
+    proofs = [(trie.prove(k), k, root) for k in keys]
+    nodes, node_off, first, keysa, _ = batch_of(proofs)
+    roots = np.frombuffer(root, np.uint8)
+    want = oracle.verify_proofs(nodes, node_off, first, keysa, roots)
+    got = gpu_verify(ctx, nodes, node_off, first, keysa, roots)
+    assert (got[1] == want[1]).all() and (want[1] == 1).all()
+
+
+@pytest.mark.parametrize("which", [2, 3])
+def test_device_synth_equals_oracle_synth(ctx, oracle, which):
+    """phant_b200/csrc/synth.cu vs oracle/synth.c: byte-identical witnesses, then identical verdicts."""
+    import torch
+    n = 2000
+    n_nodes, n_bytes = ctx.synth_sizes(which, n, depth=8, first=1000)
+    d_nodes = torch.zeros(n_bytes + 64, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(n_nodes + 1, dtype=torch.int64, device="cuda")
+    d_first = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    d_keys = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    d_roots = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    ctx.synth(which, n, d_nodes, d_off, d_first, d_keys, d_roots, depth=8, first=1000)
+    o = oracle.synth_c2(n, depth=8, first=1000) if which == 2 else oracle.synth_c3(n, first=1000)
+    assert n_bytes == int(o[1][-1]) and n_nodes == len(o[1]) - 1
+    assert (d_nodes.cpu().numpy()[:n_bytes] == o[0][:n_bytes]).all()
+    assert (d_off.cpu().numpy().astype(np.uint64) == o[1]).all()
+    assert (d_first.cpu().numpy().astype(np.uint64) == o[2]).all()
+    assert (d_keys.cpu().numpy() == o[3]).all() and (d_roots.cpu().numpy() == o[4]).all()
+    want = oracle.verify_proofs(*o, threads=8)
+    got = gpu_verify(ctx, *o)
+    assert (got[1] == want[1]).all() and (got[0] == want[0]).all()
+    expect = np.where((np.arange(n) + 1000) % 97 == 0, 0, 1)
+    assert (got[1] == expect).all()
+
+
+def test_full_size_c2_property(ctx):
+    """BASELINE config: 1M account proofs, depth 8, generated and verified in HBM; reject iff index % 97 == 0."""
+    import torch
+    from phant_b200 import gpu
+    n = 1_000_000
+    n_nodes, n_bytes = ctx.synth_sizes(2, n, depth=8)
+    assert n_bytes == n * 3836
+    d_nodes = torch.empty(n_bytes + 64, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(n_nodes + 1, dtype=torch.int64, device="cuda")
+    d_first = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    d_keys = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    d_roots = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    ctx.synth(2, n, d_nodes, d_off, d_first, d_keys, d_roots, depth=8)
+    d_status = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+    ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+    ctx.verify_proofs(n, d_nodes, d_off, d_first, d_keys, d_roots, n, d_bitmap, d_status, None, None)
+    ctx.synchronize()
+    ctx.set_flags(0)
+    st = d_status.cpu().numpy()
+    expect = np.where(np.arange(n) % 97 == 0, 0, 1)
+    assert (st == expect).all()
+    bm = d_bitmap.cpu().numpy().view(np.uint64)
+    bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[:n]
+    assert (bits == expect).all()
