@@ -4,7 +4,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
-#include <initializer_list>
+#include <array>
 
 struct phant_gpu_ctx;
 
@@ -35,7 +35,7 @@ struct phant_gpu_ctx {
     DevBuf d_b0, d_b1, d_b2, d_b3, d_b4, d_b5, d_b6, d_b7, d_b8, d_b9;    // trie builder scratch
     bool perms_init = false, perms_pending = false;
 
-    std::initializer_list<DevBuf*> all_bufs()
+    std::array<DevBuf*, 31> all_bufs()
     {
         return {&d_msgs, &d_off, &d_out, &d_first, &d_keys, &d_roots, &d_digests, &d_bitmap, &d_status, &d_voff, &d_vlen,
                 &d_cls, &d_cls2, &d_idx, &d_order, &d_cub, &d_perms, &d_tmp_a, &d_tmp_b, &d_scan_a, &d_scan_b,
