@@ -60,6 +60,10 @@ int phant_gpu_abi_version(void);
 int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg);
 void phant_gpu_destroy(phant_gpu_ctx* ctx);
 int phant_gpu_set_flags(phant_gpu_ctx* ctx, uint32_t flags);
+/* Run on the caller's CUDA stream (a cudaStream_t passed as void*) instead of the context's own; NULL
+ * restores the private stream.  With device pointers every call is then asynchronous on that stream,
+ * so the caller can order it against its own kernels / NCCL collectives without a host sync. */
+int phant_gpu_set_stream(phant_gpu_ctx* ctx, void* cuda_stream);
 const char* phant_gpu_strerror(int code);
 const char* phant_gpu_last_error(const phant_gpu_ctx* ctx); /* text of the last CUDA error on this context */
 
@@ -121,6 +125,8 @@ typedef struct {
     const uint8_t* keys32;       /* n_proofs*32 */
     const uint8_t* roots32;      /* n_roots*32 */
     uint64_t n_roots;
+    uint64_t n_nodes;            /* = proof_first[n_proofs]; may be 0 = "read it from the arrays" (host pointers: */
+    uint64_t nodes_bytes;        /* = node_off[n_nodes];      always derived; device pointers: costs a sync)      */
 } phant_gpu_proof_batch;
 int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap,
                             uint8_t* status, uint64_t* val_off, uint32_t* val_len);

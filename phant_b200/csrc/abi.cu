@@ -105,11 +105,12 @@ extern "C" int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg
     if (!ctx) return PHANT_GPU_E_OOM;
     ctx->device = dev;
     ctx->flags = cfg ? cfg->flags : 0;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return PHANT_GPU_E_CUDA;
     }
+    ctx->stream = ctx->own_stream;
     *out = ctx;
     return PHANT_GPU_OK;
 }
@@ -122,7 +123,7 @@ extern "C" void phant_gpu_destroy(phant_gpu_ctx* ctx)
     for (DevBuf* b : ctx->all_bufs()) b->release();
     for (int i = 0; i < phant_gpu_ctx::MAX_PAIRS; ++i)
         if (ctx->pairs[i].a) { cudaEventDestroy(ctx->pairs[i].a); cudaEventDestroy(ctx->pairs[i].b); }
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -130,6 +131,13 @@ extern "C" int phant_gpu_set_flags(phant_gpu_ctx* ctx, uint32_t flags)
 {
     if (!ctx) return PHANT_GPU_E_INVALID;
     ctx->flags = flags;
+    return PHANT_GPU_OK;
+}
+extern "C" int phant_gpu_set_stream(phant_gpu_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return PHANT_GPU_E_INVALID;
+    ctx->resolve_times();
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return PHANT_GPU_OK;
 }
 extern "C" const char* phant_gpu_last_error(const phant_gpu_ctx* ctx) { return ctx ? ctx->last_error : "null context"; }
@@ -261,12 +269,14 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
     const size_t bm_bytes = ((np + 63) / 64) * 8;
 
     if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) {
-        uint64_t n_nodes = 0, total = 0;
-        CU(cudaMemcpyAsync(&n_nodes, in->proof_first + np, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (n_nodes) {
-            CU(cudaMemcpyAsync(&total, in->node_off + n_nodes, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        uint64_t n_nodes = in->n_nodes, total = in->nodes_bytes;
+        if (n_nodes == 0) { // not supplied: read the tails of the CSR arrays back (one sync each)
+            CU(cudaMemcpyAsync(&n_nodes, in->proof_first + np, 8, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
+            if (n_nodes) {
+                CU(cudaMemcpyAsync(&total, in->node_off + n_nodes, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
         }
         if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
         if (int rc = ctx->hash_csr(in->nodes, in->node_off, n_nodes, total, (uint8_t*)ctx->d_digests.ptr)) return rc;

@@ -23,7 +23,8 @@ struct EventPair {
 struct phant_gpu_ctx {
     int device = 0;
     uint32_t flags = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // the stream work is issued on (own_stream unless the caller set one)
+    cudaStream_t own_stream = nullptr;
     char last_error[256] = {0};
     phant_gpu_stats stats = {};
 

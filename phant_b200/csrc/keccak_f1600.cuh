@@ -41,19 +41,18 @@ __device__ __forceinline__ uint64_t rol64(uint64_t x)
     return ((uint64_t)rhi << 32) | rlo;
 }
 
-// theta + rho + pi for one input lane: B[pi(I)] = rol(A[I] ^ D[I % 5], RHO[I])
-#define PHANT_RHOPI(I, J, R) b[J] = rol64<R>(a[I] ^ d[(I) % 5]);
+// theta + rho + pi for one input lane: B[pi(I)] = rol(A[I] ^ D[I % 5], RHO[I]) with
+// D[x] = C[x-1] ^ rol(C[x+1], 1) folded into the lane's own 3-input XOR (one LOP3 per half instead of
+// forming D first: 122 LOP3 + 58 SHF per round, measured 4.27 vs 3.99 G perm/s register-resident).
+#define PHANT_RHOPI(I, J, R) b[J] = rol64<R>(a[I] ^ c[((I) % 5 + 4) % 5] ^ r1[((I) % 5 + 1) % 5]);
 
 __device__ __forceinline__ void keccak_round(uint64_t (&a)[25], uint64_t rc)
 {
-    uint64_t c[5], d[5], b[25];
+    uint64_t c[5], r1[5], b[25];
 #pragma unroll
     for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
-    d[0] = c[4] ^ rol64<1>(c[1]);
-    d[1] = c[0] ^ rol64<1>(c[2]);
-    d[2] = c[1] ^ rol64<1>(c[3]);
-    d[3] = c[2] ^ rol64<1>(c[4]);
-    d[4] = c[3] ^ rol64<1>(c[0]);
+#pragma unroll
+    for (int x = 0; x < 5; ++x) r1[x] = rol64<1>(c[x]);
     // lane I=x+5y moves to J=y+5((2x+3y)%5) rotated by RHO[I]
     PHANT_RHOPI(0, 0, 0)    PHANT_RHOPI(1, 10, 1)   PHANT_RHOPI(2, 20, 62)  PHANT_RHOPI(3, 5, 28)   PHANT_RHOPI(4, 15, 27)
     PHANT_RHOPI(5, 16, 36)  PHANT_RHOPI(6, 1, 44)   PHANT_RHOPI(7, 11, 6)   PHANT_RHOPI(8, 21, 55)  PHANT_RHOPI(9, 6, 20)

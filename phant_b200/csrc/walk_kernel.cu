@@ -48,9 +48,37 @@ __device__ __forceinline__ uint32_t rlp_item(const uint8_t* p, uint32_t avail, I
     return (uint32_t)(1 + n + len);
 }
 
-__device__ __forceinline__ bool eq32(const uint8_t* a, const uint32_t (&e)[8])
+// 32 bytes at a 16-byte aligned address (digests, roots) as two 128-bit loads
+__device__ __forceinline__ void load32_aligned(const uint8_t* a, uint32_t (&e)[8])
 {
-    // a may be unaligned (a hash inside a node)
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(a)), hi = __ldg(reinterpret_cast<const uint4*>(a) + 1);
+    e[0] = lo.x; e[1] = lo.y; e[2] = lo.z; e[3] = lo.w;
+    e[4] = hi.x; e[5] = hi.y; e[6] = hi.z; e[7] = hi.w;
+}
+__device__ __forceinline__ bool eq32_aligned(const uint8_t* a, const uint32_t (&e)[8])
+{
+    uint32_t d[8];
+    load32_aligned(a, d);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) diff |= d[i] ^ e[i];
+    return diff == 0;
+}
+// 32 bytes at any address (a hash inside a node): aligned 32-bit loads + one funnel shift per word
+__device__ __forceinline__ void load32(const uint8_t* a, uint32_t (&e)[8])
+{
+    const uintptr_t p = (uintptr_t)a;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(p & 3) * 8;
+    uint32_t v[9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = w[i];
+    v[8] = sh ? w[8] : 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = __funnelshift_r(v[i], v[i + 1], sh);
+}
+__device__ __forceinline__ bool eq32_const(const uint8_t* a, const uint32_t (&e)[8])
+{
     uint32_t diff = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -58,12 +86,6 @@ __device__ __forceinline__ bool eq32(const uint8_t* a, const uint32_t (&e)[8])
         diff |= w ^ e[i];
     }
     return diff == 0;
-}
-__device__ __forceinline__ void load32(const uint8_t* a, uint32_t (&e)[8])
-{
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        e[i] = (uint32_t)a[4 * i] | ((uint32_t)a[4 * i + 1] << 8) | ((uint32_t)a[4 * i + 2] << 16) | ((uint32_t)a[4 * i + 3] << 24);
 }
 
 __constant__ uint8_t EMPTY_ROOT[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45,
@@ -76,8 +98,8 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
 {
     voff = 0; vlen = 0;
     uint32_t expect[8];
-    load32(root, expect);
-    if (first == last) return eq32(EMPTY_ROOT, expect) ? ST_ABSENT : ST_REJECT;
+    load32_aligned(root, expect);
+    if (first == last) return eq32_const(EMPTY_ROOT, expect) ? ST_ABSENT : ST_REJECT;
 
     uint32_t pos = 0; // nibbles of the key consumed
     uint64_t i = first;
@@ -93,7 +115,7 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
             if (l > 0xffffffffull) return ST_REJECT;
             cur = nodes + o;
             cur_len = (uint32_t)l;
-            if (!eq32(digests + 32 * i, expect)) return ST_REJECT; // R1
+            if (!eq32_aligned(digests + 32 * i, expect)) return ST_REJECT; // R1
             ++i;
         }
         Item top;

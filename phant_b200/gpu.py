@@ -39,7 +39,8 @@ class Accounts(C.Structure):
 
 class ProofBatch(C.Structure):
     _fields_ = [("n_proofs", C.c_uint64), ("nodes", C.c_void_p), ("node_off", C.c_void_p), ("proof_first", C.c_void_p),
-                ("keys32", C.c_void_p), ("roots32", C.c_void_p), ("n_roots", C.c_uint64)]
+                ("keys32", C.c_void_p), ("roots32", C.c_void_p), ("n_roots", C.c_uint64), ("n_nodes", C.c_uint64),
+                ("nodes_bytes", C.c_uint64)]
 
 
 class TrieDesc(C.Structure):
@@ -47,7 +48,7 @@ class TrieDesc(C.Structure):
 
 
 EXPORTS = [
-    "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_strerror",
+    "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_set_stream", "phant_gpu_strerror",
     "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
     "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_state_root", "phant_gpu_verify_proofs",
     "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
@@ -71,6 +72,7 @@ def _lib():
     L.phant_gpu_destroy.argtypes = [vp]
     L.phant_gpu_destroy.restype = None
     L.phant_gpu_set_flags.argtypes = [vp, C.c_uint32]
+    L.phant_gpu_set_stream.argtypes = [vp, vp]
     L.phant_gpu_strerror.argtypes = [C.c_int]
     L.phant_gpu_strerror.restype = C.c_char_p
     L.phant_gpu_last_error.argtypes = [vp]
@@ -133,6 +135,10 @@ class Context:
         self._chk(_lib().phant_gpu_set_flags(self._h, flags), "set_flags")
         self.flags = flags
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer handle (e.g. torch.cuda.current_stream().cuda_stream) or None"""
+        self._chk(_lib().phant_gpu_set_stream(self._h, cuda_stream), "set_stream")
+
     def synchronize(self):
         self._chk(_lib().phant_gpu_synchronize(self._h), "synchronize")
 
@@ -164,8 +170,9 @@ class Context:
 
     # V
     def verify_proofs(self, n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, bitmap=None, status=None,
-                      val_off=None, val_len=None):
-        b = ProofBatch(n_proofs, _ptr(nodes), _ptr(node_off), _ptr(proof_first), _ptr(keys32), _ptr(roots32), n_roots)
+                      val_off=None, val_len=None, n_nodes=0, nodes_bytes=0):
+        b = ProofBatch(n_proofs, _ptr(nodes), _ptr(node_off), _ptr(proof_first), _ptr(keys32), _ptr(roots32), n_roots,
+                       n_nodes, nodes_bytes)
         self._chk(_lib().phant_gpu_verify_proofs(self._h, C.byref(b), _ptr(bitmap), _ptr(status), _ptr(val_off), _ptr(val_len)),
                   "verify_proofs")
 
