@@ -295,8 +295,8 @@ def run_gpu(args, rank, world, local_rank):
         except (OSError, KeyError, ValueError):
             pass
         sm_mhz = clocks.get("sm_mhz") or 1900.0
-        # integer-issue ceiling of the permutation: 24 rounds x 195 ALU-pipe instructions (SASS count), 64 lanes/clk/SM
-        alu_peak_perm_s = 148 * 64 * sm_mhz * 1e6 / (24 * 195)
+        # integer-issue ceiling of the permutation: 24 rounds x 180 ALU-pipe instructions (SASS count), 64 lanes/clk/SM
+        alu_peak_perm_s = 148 * 64 * sm_mhz * 1e6 / (24 * 180)
         perm_s = st["keccak_perms"] / args.steps / (keccak_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -309,7 +309,7 @@ def run_gpu(args, rank, world, local_rank):
                          "note": "Keccak-f is integer-issue bound, not HBM bound: see alu",
                          "alu": {"achieved_gperm_s": perm_s / 1e9, "peak_gperm_s": alu_peak_perm_s / 1e9,
                                  "frac": perm_s / alu_peak_perm_s,
-                                 "model": "148 SM x 64 INT lanes/clk x sm_mhz / (24 rounds x 195 ALU instr)"}},
+                                 "model": "148 SM x 64 INT lanes/clk x sm_mhz / (24 rounds x 180 ALU instr)"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e["h2d_bytes"] // e2e_steps,
                     "d2h_bytes_per_step": st_e["d2h_bytes"] // e2e_steps, "steps": e2e_steps,
                     "ms_per_step": 1e3 * float(t_e.item()) / e2e_steps},

@@ -49,7 +49,7 @@ void DevBuf::release()
 
 void phant_gpu_ctx::time_begin(int which)
 {
-    if (n_pairs >= MAX_PAIRS) resolve_times();
+    if ((size_t)n_pairs >= pairs.size()) pairs.emplace_back();
     EventPair& p = pairs[n_pairs];
     if (!p.a) { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
     p.which = which;
@@ -111,6 +111,12 @@ extern "C" int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg
         return PHANT_GPU_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return PHANT_GPU_E_CUDA;
+    }
     *out = ctx;
     return PHANT_GPU_OK;
 }
@@ -121,8 +127,10 @@ extern "C" void phant_gpu_destroy(phant_gpu_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : ctx->all_bufs()) b->release();
-    for (int i = 0; i < phant_gpu_ctx::MAX_PAIRS; ++i)
-        if (ctx->pairs[i].a) { cudaEventDestroy(ctx->pairs[i].a); cudaEventDestroy(ctx->pairs[i].b); }
+    for (EventPair& p : ctx->pairs)
+        if (p.a) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -290,11 +298,9 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
     }
 
     // host pointers: validate the CSR arrays, stage everything, run, copy the verdicts back
+    // (the CSR arrays are validated chunk by chunk below, while the previous chunk's DMA is in flight)
     const uint64_t n_nodes = in->proof_first[np];
-    for (uint64_t p = 0; p < np; ++p)
-        if (in->proof_first[p + 1] < in->proof_first[p]) return PHANT_GPU_E_INVALID;
-    uint64_t total = 0;
-    if (int rc = check_offsets_host(in->node_off, n_nodes, &total)) return rc;
+    const uint64_t total = in->node_off[n_nodes];
     if (total && !in->nodes) return PHANT_GPU_E_INVALID;
     if (int rc = ctx->d_msgs.reserve(ctx, total + 64)) return rc;
     if (int rc = ctx->d_off.reserve(ctx, 8 * (n_nodes + 1))) return rc;
@@ -306,23 +312,66 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
     if (int rc = ctx->d_status.reserve(ctx, np)) return rc;
     if (val_off) if (int rc = ctx->d_voff.reserve(ctx, 8 * np)) return rc;
     if (val_len) if (int rc = ctx->d_vlen.reserve(ctx, 4 * np)) return rc;
-    cudaStream_t s = ctx->stream;
-    if (total) CU(cudaMemcpyAsync(ctx->d_msgs.ptr, in->nodes, total, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->d_off.ptr, in->node_off, 8 * (n_nodes + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->d_first.ptr, in->proof_first, 8 * (np + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->d_keys.ptr, in->keys32, 32 * np, cudaMemcpyHostToDevice, s));
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    // Pipeline: the witness crosses PCIe in chunks of whole proofs on the copy stream while the previous
+    // chunk is hashed and walked on the compute stream.  Device arrays keep their full size and absolute
+    // offsets, so a chunk is just a sub-range [p0, p1) of proofs = [n0, n1) of nodes = [b0, b1) of bytes.
+    uint8_t* d_nodes = (uint8_t*)ctx->d_msgs.ptr;
+    uint64_t* d_noff = (uint64_t*)ctx->d_off.ptr;
+    uint64_t* d_pfirst = (uint64_t*)ctx->d_first.ptr;
+    CU(cudaMemsetAsync(ctx->d_bitmap.ptr, 0, bm_bytes, s));
     CU(cudaMemcpyAsync(ctx->d_roots.ptr, in->roots32, 32 * in->n_roots, cudaMemcpyHostToDevice, s));
     ctx->stats.h2d_bytes += total + 8 * (n_nodes + 1) + 8 * (np + 1) + 32 * np + 32 * in->n_roots;
-    if (int rc = ctx->hash_csr((const uint8_t*)ctx->d_msgs.ptr, (const uint64_t*)ctx->d_off.ptr, n_nodes, total, (uint8_t*)ctx->d_digests.ptr))
-        return rc;
-    CU(cudaMemsetAsync(ctx->d_bitmap.ptr, 0, bm_bytes, s));
-    ctx->time_begin(1);
-    CU(launch_walk(s, ctx->device, np, (const uint8_t*)ctx->d_msgs.ptr, (const uint64_t*)ctx->d_off.ptr, (const uint64_t*)ctx->d_first.ptr,
-                   (const uint8_t*)ctx->d_keys.ptr, (const uint8_t*)ctx->d_roots.ptr, in->n_roots, (const uint8_t*)ctx->d_digests.ptr,
-                   (uint64_t*)ctx->d_bitmap.ptr, (uint8_t*)ctx->d_status.ptr, val_off ? (uint64_t*)ctx->d_voff.ptr : nullptr,
-                   val_len ? (uint32_t*)ctx->d_vlen.ptr : nullptr));
-    ctx->time_end();
-    ctx->stats.launches++;
+    const uint64_t target_bytes = 48ull << 20; // per chunk: large enough for PCIe efficiency, small enough to start early
+    uint64_t p0 = 0;
+    size_t chunk = 0;
+    // the copy stream must not overwrite buffers a previous call's kernels may still read
+    if (ctx->chunk_events.empty()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_events.push_back(e); }
+    CU(cudaEventRecord(ctx->chunk_events[0], s));
+    CU(cudaStreamWaitEvent(cs, ctx->chunk_events[0], 0));
+    while (p0 < np) {
+        // grow the chunk proof by proof (64 at a time, so bitmap words never straddle chunks) up to the byte target
+        uint64_t p1 = p0;
+        const uint64_t n0 = in->proof_first[p0], b0 = n0 <= n_nodes ? in->node_off[n0] : 0;
+        bool in_range = n0 <= n_nodes;
+        do {
+            p1 = p1 + 4096 < np ? p1 + 4096 : np;
+            in_range = in_range && in->proof_first[p1] <= n_nodes;
+        } while (in_range && p1 < np && in->node_off[in->proof_first[p1]] - b0 < target_bytes);
+        if (!in_range) { // never leave DMA running on the caller's buffers behind an error return
+            cudaStreamSynchronize(cs);
+            cudaStreamSynchronize(s);
+            return PHANT_GPU_E_INVALID;
+        }
+        const uint64_t n1 = in->proof_first[p1], b1 = in->node_off[n1];
+        {   // monotone offsets inside the declared totals, or nothing of this chunk is touched
+            bool ok = n0 <= n1 && n1 <= n_nodes && b0 <= b1 && b1 <= total;
+            for (uint64_t p = p0; ok && p < p1; ++p) ok = in->proof_first[p] <= in->proof_first[p + 1];
+            for (uint64_t j = n0; ok && j < n1; ++j) ok = in->node_off[j] <= in->node_off[j + 1];
+            if (!ok) {
+                cudaStreamSynchronize(cs);
+                cudaStreamSynchronize(s);
+                return PHANT_GPU_E_INVALID;
+            }
+        }
+        if (b1 > b0) CU(cudaMemcpyAsync(d_nodes + b0, in->nodes + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(d_noff + n0, in->node_off + n0, 8 * (n1 - n0 + 1), cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(d_pfirst + p0, in->proof_first + p0, 8 * (p1 - p0 + 1), cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync((uint8_t*)ctx->d_keys.ptr + 32 * p0, in->keys32 + 32 * p0, 32 * (p1 - p0), cudaMemcpyHostToDevice, cs));
+        ++chunk;
+        if (ctx->chunk_events.size() <= chunk) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_events.push_back(e); }
+        CU(cudaEventRecord(ctx->chunk_events[chunk], cs));
+        CU(cudaStreamWaitEvent(s, ctx->chunk_events[chunk], 0));
+        if (int rc = ctx->hash_csr(d_nodes, d_noff + n0, n1 - n0, b1 - b0, (uint8_t*)ctx->d_digests.ptr + 32 * n0)) return rc;
+        ctx->time_begin(1);
+        CU(launch_walk(s, ctx->device, p1 - p0, d_nodes, d_noff, d_pfirst + p0, (const uint8_t*)ctx->d_keys.ptr + 32 * p0,
+                       (const uint8_t*)ctx->d_roots.ptr + (in->n_roots == 1 ? 0 : 32 * p0), in->n_roots, (const uint8_t*)ctx->d_digests.ptr,
+                       (uint64_t*)ctx->d_bitmap.ptr + p0 / 64, (uint8_t*)ctx->d_status.ptr + p0, val_off ? (uint64_t*)ctx->d_voff.ptr + p0 : nullptr,
+                       val_len ? (uint32_t*)ctx->d_vlen.ptr + p0 : nullptr));
+        ctx->time_end();
+        ctx->stats.launches++;
+        p0 = p1;
+    }
     if (accept_bitmap) { CU(cudaMemcpyAsync(accept_bitmap, ctx->d_bitmap.ptr, bm_bytes, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += bm_bytes; }
     if (status) { CU(cudaMemcpyAsync(status, ctx->d_status.ptr, np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += np; }
     if (val_off) { CU(cudaMemcpyAsync(val_off, ctx->d_voff.ptr, 8 * np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += 8 * np; }

@@ -5,6 +5,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <array>
+#include <vector>
 
 struct phant_gpu_ctx;
 
@@ -44,9 +45,11 @@ struct phant_gpu_ctx {
     }
 
     // device timing of the dominant kernels: event pairs recorded on `stream`, resolved lazily
-    static constexpr int MAX_PAIRS = 64;
-    EventPair pairs[MAX_PAIRS];
+    std::vector<EventPair> pairs; // pool, grows on demand; the first n_pairs are pending
     int n_pairs = 0;
+    // host-pointer pipeline: H2D on copy_stream chunk by chunk, kernels on `stream` behind an event per chunk
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
     void time_begin(int which);
     void time_end();
     void resolve_times();

@@ -141,3 +141,28 @@ def test_full_size_c2_property(ctx):
     bm = d_bitmap.cpu().numpy().view(np.uint64)
     bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[:n]
     assert (bits == expect).all()
+
+
+def test_host_pipeline_many_chunks_and_bad_csr(ctx, oracle):
+    """host-pointer path crosses PCIe in chunks: 40k proofs (> 3 chunks) must give the same verdicts as the
+    oracle; corrupt CSR arrays must be refused with E_INVALID, not read out of bounds."""
+    from phant_b200 import gpu
+    n = 40_000
+    o = oracle.synth_c2(n, depth=8, first=7)
+    want = oracle.verify_proofs(*o, threads=8)
+    got = gpu_verify(ctx, *o)
+    assert (got[1] == want[1]).all() and (got[0] == want[0]).all()
+    nodes, node_off, first, keys, roots = o
+    bad_off = node_off.copy()
+    bad_off[12345] = bad_off[12346] + 9          # not monotone
+    with pytest.raises(gpu.PhantGpuError) as e:
+        gpu_verify(ctx, nodes, bad_off, first, keys, roots)
+    assert e.value.code == -1
+    bad_first = first.copy()
+    bad_first[20000] = first[-1] + 5              # beyond n_nodes
+    with pytest.raises(gpu.PhantGpuError) as e:
+        gpu_verify(ctx, nodes, node_off, bad_first, keys, roots)
+    assert e.value.code == -1
+    # and the context is still usable afterwards
+    got = gpu_verify(ctx, *o)
+    assert (got[1] == want[1]).all()
