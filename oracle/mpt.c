@@ -92,7 +92,7 @@ static node* make_leaf(oracle_trie* t, const uint8_t* path, uint32_t plen, const
     nd->kind = K_LEAF;
     nd->path = path;
     nd->path_len = plen;
-    uint8_t hp[40];
+    uint8_t* hp = malloc(plen / 2 + 2);
     uint32_t hpn = hex_prefix(hp, path, plen, 1);
     uint64_t payload = rlp_str_size(hp, hpn) + rlp_str_size(val, vlen);
     nd->rlp = malloc(rlp_list_hdr_size(payload) + payload);
@@ -100,6 +100,7 @@ static node* make_leaf(oracle_trie* t, const uint8_t* path, uint32_t plen, const
     o += rlp_put_str(nd->rlp + o, hp, hpn);
     o += rlp_put_str(nd->rlp + o, val, vlen);
     nd->rlp_len = o;
+    free(hp);
     finish(t, nd);
     return nd;
 }
@@ -143,7 +144,7 @@ static node* insert_node(oracle_trie* t, uint64_t lo, uint64_t hi, uint32_t leve
             en->path = NIB(t, lo) + level;
             en->path_len = pi - level;
             en->next = next;
-            uint8_t hp[40];
+            uint8_t* hp = malloc(en->path_len / 2 + 2);
             uint32_t hpn = hex_prefix(hp, en->path, en->path_len, 0);
             uint64_t payload = rlp_str_size(hp, hpn) + ref_size(next);
             en->rlp = malloc(rlp_list_hdr_size(payload) + payload);
@@ -151,6 +152,7 @@ static node* insert_node(oracle_trie* t, uint64_t lo, uint64_t hi, uint32_t leve
             o += rlp_put_str(en->rlp + o, hp, hpn);
             o += put_ref(en->rlp + o, next);
             en->rlp_len = o;
+            free(hp);
             finish(t, en);
             return en;
         }

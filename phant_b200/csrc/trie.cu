@@ -1,9 +1,1159 @@
-// trie.cu -- builders: M (mptize), S (state root), U (resident trie).  PLACEHOLDER: not implemented yet.
+// trie.cu -- trie builders on the device: M (== mptize), S (state root), U (resident complete trie).
+//
+// M restates src/mpt/mpt.zig:38-314 as a level-synchronous FOREST builder over sorted keys:
+//   top-down   every (extension+)branch unit is a key range [lo, hi) of the sorted list; its branch depth is the
+//              common prefix of the range (mpt.zig:83-106), a key that ends there is the branch value
+//              (mpt.zig:65-69), and the 16 children are found by binary search on the next nibble
+//              (mpt.zig:72-79) -- 16 threads per unit, one BFS level per launch;
+//   bottom-up  leaves first, then unit levels deepest-first: RLP is written into a scratch arena
+//              (leaf mpt.zig:255-281, branch :218-247, extension :180-209, hex-prefix :285-314) and hashed by
+//              the SAME batched Keccak kernel the verifier uses; a child enters its parent as raw RLP when
+//              < 32 bytes, else as its hash (mpt.zig:104,112); the root is always hashed (mpt.zig:42).
+// A forest (many tries at once) is what S needs: all storage tries of a state are built together.
+// S follows evmone/test/state/mpt_hash.cpp:15-36 for the trie contents (phant has no StateDB.root()).
+// U is the dirty-frontier recompute over a resident complete 16-ary trie (BASELINE.json config C4).
 #include "../../include/phant_gpu.h"
+#include "common.cuh"
 #include "ctx.cuh"
-extern "C" int phant_gpu_mpt_root(phant_gpu_ctx*, const uint8_t*, const uint32_t*, const uint8_t*, const uint64_t*, uint64_t, uint8_t*) { return PHANT_GPU_E_INVALID; }
-extern "C" int phant_gpu_state_root(phant_gpu_ctx*, const phant_gpu_accounts*, uint8_t*) { return PHANT_GPU_E_INVALID; }
-extern "C" int phant_gpu_trie_open(phant_gpu_ctx*, const phant_gpu_trie_desc*, phant_gpu_trie**) { return PHANT_GPU_E_INVALID; }
-extern "C" int phant_gpu_trie_root(phant_gpu_trie*, uint8_t*) { return PHANT_GPU_E_INVALID; }
-extern "C" int phant_gpu_trie_update(phant_gpu_trie*, const uint8_t*, const uint8_t*, const uint32_t*, uint64_t, uint8_t*) { return PHANT_GPU_E_INVALID; }
-extern "C" void phant_gpu_trie_close(phant_gpu_trie*) {}
+#include "keccak_f1600.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <string.h>
+#include <new>
+#include <vector>
+
+using namespace phant;
+
+#define CU(expr)                                                                \
+    do {                                                                        \
+        cudaError_t e_ = (expr);                                                \
+        if (e_ != cudaSuccess) return ctx->fail(e_, #expr, __FILE__, __LINE__); \
+    } while (0)
+#define RC(expr)                  \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+namespace {
+
+constexpr uint32_t NONE = 0xffffffffu;
+constexpr uint32_t KIND_LEAF = 1u << 30, KIND_NODE = 2u << 30, KIND_MASK = 3u << 30, IDX_MASK = ~KIND_MASK;
+
+__constant__ uint8_t EMPTY_ROOT_D[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45,
+                                         0xe6, 0x92, 0xc0, 0xf8, 0x6e, 0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c,
+                                         0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+
+// ---------------------------------------------------------------- RLP helpers (device)
+__device__ __forceinline__ uint32_t be_len(uint64_t v)
+{
+    uint32_t n = 0;
+    while (v) { ++n; v >>= 8; }
+    return n;
+}
+__device__ __forceinline__ uint64_t str_size(uint64_t len, uint32_t first_byte)
+{
+    if (len == 1 && first_byte < 0x80) return 1;
+    if (len <= 55) return 1 + len;
+    return 1 + be_len(len) + len;
+}
+__device__ __forceinline__ uint32_t hdr_size(uint64_t payload) { return payload <= 55 ? 1 : 1 + be_len(payload); }
+__device__ __forceinline__ uint32_t put_hdr(uint8_t* out, uint64_t len, uint32_t short_base, uint32_t long_base)
+{
+    if (len <= 55) { out[0] = (uint8_t)(short_base + len); return 1; }
+    const uint32_t n = be_len(len);
+    out[0] = (uint8_t)(long_base + n);
+    for (uint32_t i = 0; i < n; ++i) out[1 + i] = (uint8_t)(len >> (8 * (n - 1 - i)));
+    return 1 + n;
+}
+
+// ---------------------------------------------------------------- key access
+struct Keys {
+    const uint8_t* bytes;
+    const uint32_t* off; // n+1
+};
+__device__ __forceinline__ uint32_t nlen(const Keys& k, uint32_t i) { return 2 * (k.off[i + 1] - k.off[i]); }
+__device__ __forceinline__ uint32_t nib(const Keys& k, uint32_t i, uint32_t pos)
+{
+    const uint8_t b = k.bytes[k.off[i] + (pos >> 1)];
+    return (pos & 1) ? (b & 15u) : (b >> 4);
+}
+// common prefix of keys i and j in nibbles
+__device__ uint32_t lcp(const Keys& k, uint32_t i, uint32_t j)
+{
+    const uint32_t li = k.off[i + 1] - k.off[i], lj = k.off[j + 1] - k.off[j];
+    const uint32_t m = li < lj ? li : lj;
+    const uint8_t* a = k.bytes + k.off[i];
+    const uint8_t* b = k.bytes + k.off[j];
+    uint32_t t = 0;
+    while (t < m && a[t] == b[t]) ++t;
+    if (t == m) return 2 * m;
+    return 2 * t + (((a[t] ^ b[t]) & 0xf0) ? 0 : 1);
+}
+// hex-prefix bytes of nibbles [from, to) of key i (mpt.zig:285-314); returns count
+__device__ uint32_t hp_size(uint32_t cnt) { return 1 + cnt / 2; }
+__device__ uint32_t put_hp(uint8_t* out, const Keys& k, uint32_t i, uint32_t from, uint32_t to, bool leaf)
+{
+    const uint32_t cnt = to - from;
+    uint32_t o = 0, q = from;
+    if (cnt & 1) { out[o++] = (uint8_t)(((leaf ? 3 : 1) << 4) | nib(k, i, q)); ++q; }
+    else out[o++] = (uint8_t)((leaf ? 2 : 0) << 4);
+    for (; q < to; q += 2) out[o++] = (uint8_t)((nib(k, i, q) << 4) | nib(k, i, q + 1));
+    return o;
+}
+__device__ uint32_t hp_first_byte(const Keys& k, uint32_t i, uint32_t from, uint32_t to, bool leaf)
+{
+    const uint32_t cnt = to - from;
+    return (cnt & 1) ? (((leaf ? 3u : 1u) << 4) | nib(k, i, from)) : ((leaf ? 2u : 0u) << 4);
+}
+
+// ---------------------------------------------------------------- node tables
+struct Tables {
+    // per unit (capacity = n_keys)
+    uint32_t *lo, *hi, *ext_from, *depth, *child; // child[16 * id + v]
+    uint8_t* has_value;
+    uint32_t* ext_list; // per level: ids of units with an extension, at the level's base
+    // per key
+    uint32_t* leaf_start; // nibble where the leaf path starts; NONE for branch-value keys
+    // references (what a parent copies): 33 bytes + length, for leaves [0, n) and units [n, n + cap)
+    uint8_t* ref;
+    uint8_t* ref_len;
+    uint8_t* top_digest; // per unit: hash of its topmost encoding (extension if any, else branch)
+    // per segment
+    uint32_t* seg_root; // KIND | idx, or 0 = empty
+};
+
+// ---------------------------------------------------------------- validation
+__global__ void check_sorted_kernel(Keys k, const uint32_t* __restrict__ seg_of_key, uint32_t n, uint32_t* bad)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.x * blockDim.x) {
+        if (seg_of_key && seg_of_key[i] != seg_of_key[i + 1]) continue;
+        const uint32_t la = k.off[i + 1] - k.off[i], lb = k.off[i + 2] - k.off[i + 1];
+        const uint8_t* a = k.bytes + k.off[i];
+        const uint8_t* b = k.bytes + k.off[i + 1];
+        const uint32_t m = la < lb ? la : lb;
+        uint32_t t = 0;
+        while (t < m && a[t] == b[t]) ++t;
+        const bool ok = t < m ? a[t] < b[t] : la < lb; // strictly increasing; a strict prefix sorts first
+        if (!ok) atomicExch(bad, 1u);
+    }
+}
+
+// ---------------------------------------------------------------- top-down
+__global__ void init_roots_kernel(const uint32_t* __restrict__ seg_off, uint32_t n_seg, Tables t, uint32_t* counters /*[0]=units*/)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) {
+        const uint32_t lo = seg_off[s], hi = seg_off[s + 1];
+        if (hi == lo) { t.seg_root[s] = 0; continue; }
+        if (hi - lo == 1) { t.seg_root[s] = KIND_LEAF | lo; t.leaf_start[lo] = 0; continue; }
+        const uint32_t id = atomicAdd(&counters[0], 1u);
+        t.lo[id] = lo; t.hi[id] = hi; t.ext_from[id] = 0;
+        t.seg_root[s] = KIND_NODE | id;
+    }
+}
+
+// 16 threads per unit of the current level [beg, beg + cnt): find the branch depth, the branch value and the 16
+// child ranges; children with >= 2 keys become units of the next level.
+__global__ void __launch_bounds__(128)
+expand_kernel(Keys k, Tables t, uint32_t beg, uint32_t cnt, uint32_t next_base, uint32_t* counters /*[1]=next units, [2]=ext in this level*/)
+{
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t v = threadIdx.x & 15;
+    const uint32_t sub = 0xffffu << (threadIdx.x & 16); // my half-warp
+    for (uint32_t u = gid >> 4; u < cnt; u += (gridDim.x * blockDim.x) >> 4) { // the 16 lanes of a half-warp share u
+        const uint32_t id = beg + u;
+        const uint32_t lo = t.lo[id], hi = t.hi[id], from = t.ext_from[id];
+        uint32_t p = 0;
+        if (v == 0) {
+            p = lcp(k, lo, hi - 1);
+            const uint32_t l0 = nlen(k, lo);
+            if (l0 < p) p = l0;
+        }
+        p = __shfl_sync(sub, p, 0, 16);
+        const bool has_value = nlen(k, lo) == p;
+        const uint32_t first = lo + (has_value ? 1 : 0);
+        // lower bound of nibble value v at depth p within [first, hi)
+        uint32_t a = first, b = hi;
+        while (a < b) {
+            const uint32_t mid = (a + b) >> 1;
+            if (nib(k, mid, p) < v) a = mid + 1; else b = mid;
+        }
+        uint32_t ub = __shfl_down_sync(sub, a, 1, 16);
+        if (v == 15) ub = hi;
+        uint32_t child = 0;
+        const uint32_t c = ub - a;
+        if (c == 1) {
+            child = KIND_LEAF | a;
+            t.leaf_start[a] = p + 1;
+        } else if (c >= 2) {
+            const uint32_t nid = next_base + atomicAdd(&counters[1], 1u);
+            t.lo[nid] = a; t.hi[nid] = ub; t.ext_from[nid] = p + 1;
+            child = KIND_NODE | nid;
+        }
+        t.child[16 * id + v] = child;
+        if (v == 0) {
+            t.depth[id] = p;
+            t.has_value[id] = has_value ? 1 : 0;
+            if (has_value) t.leaf_start[lo] = NONE;
+            if (p > from) t.ext_list[beg + atomicAdd(&counters[2], 1u)] = id;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- leaves
+struct Vals {
+    const uint8_t* bytes;
+    const uint64_t* off;
+};
+
+__global__ void leaf_size_kernel(Keys k, Vals vals, Tables t, uint32_t n, uint64_t* __restrict__ size)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t ls = t.leaf_start[i];
+        uint64_t sz = 0;
+        if (ls != NONE) {
+            const uint32_t nl = nlen(k, i);
+            const uint32_t hpn = hp_size(nl - ls);
+            const uint64_t vl = vals.off[i + 1] - vals.off[i];
+            const uint64_t payload = str_size(hpn, hp_first_byte(k, i, ls, nl, true)) + str_size(vl, vl ? vals.bytes[vals.off[i]] : 0);
+            sz = hdr_size(payload) + payload;
+        }
+        size[i] = sz;
+    }
+}
+// one warp per leaf: lane 0 writes the headers and the path, all lanes copy the value
+__global__ void __launch_bounds__(256)
+leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t ls = t.leaf_start[i];
+        if (ls == NONE) continue;
+        uint8_t* out = arena + aoff[i];
+        const uint32_t nl = nlen(k, i);
+        const uint32_t hpn = hp_size(nl - ls);
+        const uint64_t vl = vals.off[i + 1] - vals.off[i];
+        const uint8_t* v = vals.bytes + vals.off[i];
+        const uint32_t hp0 = hp_first_byte(k, i, ls, nl, true);
+        const uint64_t s_hp = str_size(hpn, hp0), s_v = str_size(vl, vl ? v[0] : 0);
+        const uint32_t h = hdr_size(s_hp + s_v);
+        if (lane == 0) {
+            put_hdr(out, s_hp + s_v, 0xc0, 0xf7);
+            uint8_t* q = out + h;
+            if (s_hp > hpn) q += put_hdr(q, hpn, 0x80, 0xb7);
+            put_hp(q, k, i, ls, nl, true);
+            q = out + h + s_hp;
+            if (s_v > vl) put_hdr(q, vl, 0x80, 0xb7);
+        }
+        uint8_t* dst = out + h + s_hp + (s_v - vl);
+        for (uint64_t b = lane; b < vl; b += 32) dst[b] = v[b];
+    }
+}
+// reference of item j (leaf or encoded unit): raw RLP when < 32 bytes, else 0xa0 || digest
+__global__ void finalize_ref_kernel(uint32_t cnt, const uint32_t* __restrict__ ids /*nullable: identity*/, uint32_t id_base,
+                                    const uint64_t* __restrict__ aoff, const uint8_t* __restrict__ arena,
+                                    const uint8_t* __restrict__ digests, uint32_t ref_base, Tables t, uint8_t* __restrict__ top_digest)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+        const uint32_t id = ids ? ids[j] : id_base + j;
+        const uint64_t len = aoff[j + 1] - aoff[j];
+        uint8_t* r = t.ref + 33ull * (ref_base + id);
+        if (len == 0) { t.ref_len[ref_base + id] = 0; continue; } // not a leaf (branch-value key)
+        if (len < 32) {
+            for (uint32_t b = 0; b < len; ++b) r[b] = arena[aoff[j] + b];
+            t.ref_len[ref_base + id] = (uint8_t)len;
+        } else {
+            r[0] = 0xa0;
+            for (uint32_t b = 0; b < 32; ++b) r[1 + b] = digests[32ull * j + b];
+            t.ref_len[ref_base + id] = 33;
+        }
+        if (top_digest)
+            for (uint32_t b = 0; b < 32; ++b) top_digest[32ull * id + b] = digests[32ull * j + b];
+    }
+}
+
+// ---------------------------------------------------------------- branches and extensions
+__device__ __forceinline__ uint32_t child_ref_index(uint32_t child, uint32_t n_keys)
+{
+    return (child & KIND_MASK) == KIND_LEAF ? (child & IDX_MASK) : n_keys + (child & IDX_MASK);
+}
+__global__ void branch_size_kernel(Keys k, Vals vals, Tables t, uint32_t n_keys, uint32_t beg, uint32_t cnt, uint64_t* __restrict__ size)
+{
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < cnt; u += gridDim.x * blockDim.x) {
+        const uint32_t id = beg + u;
+        uint64_t payload = 0;
+        for (uint32_t v = 0; v < 16; ++v) {
+            const uint32_t c = t.child[16 * id + v];
+            payload += c ? t.ref_len[child_ref_index(c, n_keys)] : 1;
+        }
+        if (t.has_value[id]) {
+            const uint32_t i = t.lo[id];
+            const uint64_t vl = vals.off[i + 1] - vals.off[i];
+            payload += str_size(vl, vl ? vals.bytes[vals.off[i]] : 0);
+        } else payload += 1;
+        size[u] = hdr_size(payload) + payload;
+    }
+}
+// one warp per unit: lane v < 16 places child v at the prefix sum of the reference sizes, all lanes copy the value
+__global__ void __launch_bounds__(256)
+branch_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n_keys, uint32_t beg, uint32_t cnt, const uint64_t* __restrict__ aoff,
+                     uint8_t* __restrict__ arena)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < cnt; u += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t id = beg + u;
+        uint8_t* out = arena + aoff[u];
+        const uint64_t total = aoff[u + 1] - aoff[u];
+        uint32_t c = 0, sz = 0, ri = 0;
+        if (lane < 16) {
+            c = t.child[16 * id + lane];
+            if (c) { ri = child_ref_index(c, n_keys); sz = t.ref_len[ri]; } else sz = 1;
+        }
+        uint32_t pre = sz; // inclusive scan over lanes 0..15
+        for (int o = 1; o < 16; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= (uint32_t)o) pre += y;
+        }
+        const uint32_t refs_total = __shfl_sync(0xffffffffu, pre, 15);
+        const uint64_t payload_wo_value = refs_total;
+        // total = header + payload: the header size (1..5) is the one consistent with the payload it leaves
+        uint32_t hdr = 1;
+        for (uint32_t cand = 1; cand <= 5; ++cand) {
+            const uint64_t pay = total - cand;
+            if (hdr_size(pay) == cand) { hdr = cand; break; }
+        }
+        if (lane == 0) put_hdr(out, total - hdr, 0xc0, 0xf7);
+        if (lane < 16) {
+            uint8_t* q = out + hdr + (pre - sz);
+            if (c) {
+                const uint8_t* r = t.ref + 33ull * ri;
+                for (uint32_t b = 0; b < sz; ++b) q[b] = r[b];
+            } else q[0] = 0x80;
+        }
+        uint8_t* q = out + hdr + payload_wo_value;
+        if (t.has_value[id]) {
+            const uint32_t i = t.lo[id];
+            const uint64_t vl = vals.off[i + 1] - vals.off[i];
+            const uint8_t* v = vals.bytes + vals.off[i];
+            const uint64_t s_v = str_size(vl, vl ? v[0] : 0);
+            if (lane == 0 && s_v > vl) put_hdr(q, vl, 0x80, 0xb7);
+            uint8_t* dst = q + (s_v - vl);
+            for (uint64_t b = lane; b < vl; b += 32) dst[b] = v[b];
+        } else if (lane == 0) q[0] = 0x80;
+    }
+}
+__global__ void ext_size_kernel(Keys k, Tables t, uint32_t n_keys, const uint32_t* __restrict__ ids, uint32_t cnt, uint64_t* __restrict__ size)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+        const uint32_t id = ids[j];
+        const uint32_t from = t.ext_from[id], to = t.depth[id], i = t.lo[id];
+        const uint32_t hpn = hp_size(to - from);
+        const uint64_t payload = str_size(hpn, hp_first_byte(k, i, from, to, false)) + t.ref_len[n_keys + id];
+        size[j] = hdr_size(payload) + payload;
+    }
+}
+__global__ void ext_encode_kernel(Keys k, Tables t, uint32_t n_keys, const uint32_t* __restrict__ ids, uint32_t cnt,
+                                  const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+        const uint32_t id = ids[j];
+        const uint32_t from = t.ext_from[id], to = t.depth[id], i = t.lo[id];
+        const uint32_t hpn = hp_size(to - from);
+        const uint64_t s_hp = str_size(hpn, hp_first_byte(k, i, from, to, false));
+        const uint32_t rl = t.ref_len[n_keys + id];
+        uint8_t* out = arena + aoff[j];
+        uint8_t* q = out + put_hdr(out, s_hp + rl, 0xc0, 0xf7);
+        if (s_hp > hpn) q += put_hdr(q, hpn, 0x80, 0xb7);
+        q += put_hp(q, k, i, from, to, false);
+        const uint8_t* r = t.ref + 33ull * (n_keys + id);
+        for (uint32_t b = 0; b < rl; ++b) q[b] = r[b];
+    }
+}
+__global__ void gather_roots_kernel(Tables t, uint32_t n_seg, const uint8_t* __restrict__ leaf_digests, uint8_t* __restrict__ roots)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) {
+        const uint32_t r = t.seg_root[s];
+        const uint8_t* src = EMPTY_ROOT_D;
+        if ((r & KIND_MASK) == KIND_LEAF) src = leaf_digests + 32ull * (r & IDX_MASK);
+        else if ((r & KIND_MASK) == KIND_NODE) src = t.top_digest + 32ull * (r & IDX_MASK);
+        for (uint32_t b = 0; b < 32; ++b) roots[32ull * s + b] = src[b];
+    }
+}
+
+unsigned grid1d(int device, uint64_t work_items, unsigned block, unsigned per_item = 1)
+{
+    uint64_t blocks = (work_items * per_item + block - 1) / block;
+    const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks ? blocks : 1);
+}
+
+// exclusive scan of cnt u64 sizes into cnt+1 offsets (in[cnt] must be readable; it is forced to 0 first)
+int scan_sizes(phant_gpu_ctx* ctx, uint64_t* sizes, uint64_t* offs, uint64_t cnt)
+{
+    CU(cudaMemsetAsync(sizes + cnt, 0, 8, ctx->stream));
+    size_t temp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, temp, (const uint64_t*)sizes, offs, (int64_t)(cnt + 1), ctx->stream));
+    RC(ctx->d_cub.reserve(ctx, temp));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.ptr, temp, (const uint64_t*)sizes, offs, (int64_t)(cnt + 1), ctx->stream));
+    return 0;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// forest builder: keys/vals on the device, keys sorted inside each segment; roots = n_seg * 32 bytes (device)
+// ------------------------------------------------------------------------------------------------
+int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off,
+                                uint32_t n, const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots)
+{
+    phant_gpu_ctx* ctx = this;
+    cudaStream_t s = stream;
+    if (n_seg == 0) return PHANT_GPU_OK;
+    const Keys k{d_keys, d_key_off};
+    const Vals vals{d_vals, d_val_off};
+    const uint32_t cap = n ? n : 1;
+
+    // tables
+    RC(d_b0.reserve(ctx, 4ull * cap * 4 + 16ull * 4 * cap + cap)); // lo,hi,ext_from,depth + child + has_value
+    uint32_t* base = (uint32_t*)d_b0.ptr;
+    Tables t;
+    t.lo = base; t.hi = base + cap; t.ext_from = base + 2ull * cap; t.depth = base + 3ull * cap;
+    t.child = base + 4ull * cap;
+    t.has_value = (uint8_t*)(base + 20ull * cap);
+    RC(d_b1.reserve(ctx, 4ull * cap * 2 + 4ull * n_seg)); // ext_list, leaf_start, seg_root
+    t.ext_list = (uint32_t*)d_b1.ptr;
+    t.leaf_start = t.ext_list + cap;
+    t.seg_root = t.leaf_start + cap;
+    RC(d_b2.reserve(ctx, 34ull * 2 * cap + 32ull * cap)); // ref, ref_len, top_digest
+    t.ref = (uint8_t*)d_b2.ptr;
+    t.ref_len = t.ref + 33ull * 2 * cap;
+    t.top_digest = t.ref_len + 2ull * cap;
+    RC(d_b3.reserve(ctx, 64)); // counters
+    uint32_t* counters = (uint32_t*)d_b3.ptr;
+    CU(cudaMemsetAsync(counters, 0, 64, s));
+    CU(cudaMemsetAsync(t.leaf_start, 0xff, 4ull * cap, s));
+
+    // keys must be strictly sorted inside each segment (mpt.zig:39 asserts)
+    if (n > 1) {
+        check_sorted_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, d_seg_of_key, n, counters + 4);
+        stats.launches++;
+    }
+    init_roots_kernel<<<grid1d(device, n_seg, 256), 256, 0, s>>>(d_seg_off, n_seg, t, counters);
+    stats.launches++;
+    uint32_t h[8];
+    CU(cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (h[4]) return PHANT_GPU_E_INVALID;
+
+    // ---- top-down: one launch per BFS level ----
+    std::vector<uint32_t> level_beg, level_cnt, level_ext;
+    uint32_t beg = 0, cnt = h[0];
+    while (cnt) {
+        CU(cudaMemsetAsync(counters + 1, 0, 8, s));
+        expand_kernel<<<grid1d(device, cnt, 128, 16), 128, 0, s>>>(k, t, beg, cnt, beg + cnt, counters);
+        stats.launches++;
+        CU(cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        level_beg.push_back(beg); level_cnt.push_back(cnt); level_ext.push_back(h[2]);
+        beg += cnt;
+        cnt = h[1];
+        if ((uint64_t)beg + cnt > cap) return PHANT_GPU_E_CUDA; // cannot happen: a trie over n keys has < n branch units
+    }
+
+    // ---- leaves: sizes -> offsets -> encode -> hash -> references ----
+    uint8_t* leaf_digests = nullptr;
+    if (n) {
+        RC(d_b4.reserve(ctx, 8ull * (n + 1) * 2));
+        uint64_t* sizes = (uint64_t*)d_b4.ptr;
+        uint64_t* offs = sizes + (n + 1);
+        leaf_size_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, vals, t, n, sizes);
+        RC(scan_sizes(ctx, sizes, offs, n));
+        uint64_t total = 0;
+        CU(cudaMemcpyAsync(&total, offs + n, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        RC(d_b5.reserve(ctx, total + 64));
+        RC(d_b6.reserve(ctx, 32ull * n));
+        leaf_digests = (uint8_t*)d_b6.ptr;
+        leaf_encode_kernel<<<grid1d(device, n, 256, 32), 256, 0, s>>>(k, vals, t, n, offs, (uint8_t*)d_b5.ptr);
+        stats.launches += 2;
+        RC(hash_csr((const uint8_t*)d_b5.ptr, offs, n, total, leaf_digests));
+        finalize_ref_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(n, nullptr, 0, offs, (const uint8_t*)d_b5.ptr, leaf_digests, 0, t, nullptr);
+        stats.launches++;
+    }
+
+    // ---- units, deepest level first: branch, then the extension above it where there is one ----
+    for (int L = (int)level_beg.size() - 1; L >= 0; --L) {
+        const uint32_t lb = level_beg[L], lc = level_cnt[L], le = level_ext[L];
+        RC(d_b7.reserve(ctx, 8ull * (lc + 1) * 2));
+        uint64_t* sizes = (uint64_t*)d_b7.ptr;
+        uint64_t* offs = sizes + (lc + 1);
+        branch_size_kernel<<<grid1d(device, lc, 128), 128, 0, s>>>(k, vals, t, n, lb, lc, sizes);
+        RC(scan_sizes(ctx, sizes, offs, lc));
+        uint64_t total = 0;
+        CU(cudaMemcpyAsync(&total, offs + lc, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        RC(d_b8.reserve(ctx, total + 64));
+        RC(d_b9.reserve(ctx, 32ull * lc));
+        branch_encode_kernel<<<grid1d(device, lc, 256, 32), 256, 0, s>>>(k, vals, t, n, lb, lc, offs, (uint8_t*)d_b8.ptr);
+        stats.launches += 2;
+        RC(hash_csr((const uint8_t*)d_b8.ptr, offs, lc, total, (uint8_t*)d_b9.ptr));
+        finalize_ref_kernel<<<grid1d(device, lc, 256), 256, 0, s>>>(lc, nullptr, lb, offs, (const uint8_t*)d_b8.ptr, (const uint8_t*)d_b9.ptr, n, t,
+                                                                  t.top_digest);
+        stats.launches++;
+        if (le) {
+            const uint32_t* ids = t.ext_list + lb;
+            ext_size_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, sizes);
+            RC(scan_sizes(ctx, sizes, offs, le));
+            CU(cudaMemcpyAsync(&total, offs + le, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            RC(d_b8.reserve(ctx, total + 64));
+            ext_encode_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, offs, (uint8_t*)d_b8.ptr);
+            stats.launches += 2;
+            RC(hash_csr((const uint8_t*)d_b8.ptr, offs, le, total, (uint8_t*)d_b9.ptr));
+            finalize_ref_kernel<<<grid1d(device, le, 256), 256, 0, s>>>(le, ids, 0, offs, (const uint8_t*)d_b8.ptr, (const uint8_t*)d_b9.ptr, n, t,
+                                                                      t.top_digest);
+            stats.launches++;
+        }
+    }
+    gather_roots_kernel<<<grid1d(device, n_seg, 128), 128, 0, s>>>(t, n_seg, leaf_digests, d_roots);
+    stats.launches++;
+    CU(cudaGetLastError());
+    return PHANT_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// M
+// ------------------------------------------------------------------------------------------------
+extern "C" int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const uint32_t* key_off, const uint8_t* vals,
+                                  const uint64_t* val_off, uint64_t n, uint8_t out_root[32])
+{
+    if (!ctx || !out_root || (n && (!key_off || !val_off))) return PHANT_GPU_E_INVALID;
+    if (n >= (1ull << 30)) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    static const uint8_t EMPTY[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                      0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+    if (n == 0) { memcpy(out_root, EMPTY, 32); return PHANT_GPU_OK; }
+    cudaStream_t s = ctx->stream;
+    const uint8_t* d_keys = keys; const uint32_t* d_koff = key_off; const uint8_t* d_vals = vals; const uint64_t* d_voff = val_off;
+    if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS)) {
+        for (uint64_t i = 0; i < n; ++i)
+            if (key_off[i + 1] < key_off[i] || val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
+        const uint64_t kb = key_off[n], vb = val_off[n];
+        if ((kb && !keys) || (vb && !vals)) return PHANT_GPU_E_INVALID;
+        RC(ctx->d_msgs.reserve(ctx, kb + vb + 128));
+        RC(ctx->d_off.reserve(ctx, 4 * (n + 1) + 8 * (n + 1) + 16));
+        uint8_t* dk = (uint8_t*)ctx->d_msgs.ptr;
+        uint8_t* dv = dk + ((kb + 63) & ~63ull);
+        uint64_t* dvo = (uint64_t*)ctx->d_off.ptr;
+        uint32_t* dko = (uint32_t*)(dvo + (n + 1));
+        if (kb) CU(cudaMemcpyAsync(dk, keys, kb, cudaMemcpyHostToDevice, s));
+        if (vb) CU(cudaMemcpyAsync(dv, vals, vb, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dko, key_off, 4 * (n + 1), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dvo, val_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += kb + vb + 12 * (n + 1);
+        d_keys = dk; d_koff = dko; d_vals = dv; d_voff = dvo;
+    }
+    RC(ctx->d_first.reserve(ctx, 64));
+    uint32_t seg[2] = {0, (uint32_t)n};
+    CU(cudaMemcpyAsync(ctx->d_first.ptr, seg, 8, cudaMemcpyHostToDevice, s));
+    RC(ctx->d_roots.reserve(ctx, 32));
+    RC(ctx->build_forest(d_keys, d_koff, d_vals, d_voff, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr));
+    CU(cudaMemcpyAsync(out_root, ctx->d_roots.ptr, 32, cudaMemcpyDeviceToHost, s));
+    ctx->stats.d2h_bytes += 32;
+    CU(cudaStreamSynchronize(s));
+    return PHANT_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S: state root
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// non-zero slots -> (segment = account, hashed key index); also the rlp(trim(value)) size
+__global__ void slot_flag_kernel(const uint8_t* __restrict__ vals32, uint64_t n_slots, uint8_t* __restrict__ keep)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4* p = reinterpret_cast<const uint4*>(vals32 + 32 * i);
+        const uint4 a = p[0], b = p[1];
+        keep[i] = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) ? 1 : 0;
+    }
+}
+__global__ void slot_account_kernel(const uint64_t* __restrict__ slot_off, uint32_t n_acc, uint32_t* __restrict__ acc_of_slot)
+{
+    // one warp per account, lanes stride over its slots
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_acc; a += (gridDim.x * blockDim.x) >> 5)
+        for (uint64_t s = slot_off[a] + lane; s < slot_off[a + 1]; s += 32) acc_of_slot[s] = a;
+}
+// key word w (0 = most significant 8 bytes, big endian) of the 32-byte hashes, for the LSD radix passes
+__global__ void key_word_kernel(const uint8_t* __restrict__ hashes, const uint32_t* __restrict__ perm, uint32_t n, uint32_t w,
+                                uint64_t* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t* h = hashes + 32ull * perm[i] + 8 * w;
+        uint64_t v = 0;
+        for (int b = 0; b < 8; ++b) v = (v << 8) | h[b];
+        out[i] = v;
+    }
+}
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = src[perm[i]];
+}
+__global__ void iota_kernel(uint32_t* p, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+}
+__global__ void storage_value_size_kernel(const uint8_t* __restrict__ vals32, const uint32_t* __restrict__ slot_of_sorted, uint32_t n,
+                                          uint64_t* __restrict__ size)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t* v = vals32 + 32ull * slot_of_sorted[i];
+        uint32_t z = 0;
+        while (z < 32 && v[z] == 0) ++z;
+        const uint32_t len = 32 - z;
+        size[i] = (len == 1 && v[z] < 0x80) ? 1 : 1 + len;
+    }
+}
+__global__ void storage_fill_kernel(const uint8_t* __restrict__ slot_hash, const uint8_t* __restrict__ vals32,
+                                    const uint32_t* __restrict__ slot_of_sorted, uint32_t n, const uint64_t* __restrict__ val_off,
+                                    uint8_t* __restrict__ keys_out, uint32_t* __restrict__ key_off, uint8_t* __restrict__ vals_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+        key_off[i] = 32u * i;
+        if (i == n) break;
+        const uint32_t sl = slot_of_sorted[i];
+        for (int b = 0; b < 32; ++b) keys_out[32ull * i + b] = slot_hash[32ull * sl + b];
+        const uint8_t* v = vals32 + 32ull * sl;
+        uint32_t z = 0;
+        while (z < 32 && v[z] == 0) ++z;
+        const uint32_t len = 32 - z;
+        uint8_t* o = vals_out + val_off[i];
+        if (!(len == 1 && v[z] < 0x80)) *o++ = (uint8_t)(0x80 + len);
+        for (uint32_t b = 0; b < len; ++b) o[b] = v[z + b];
+    }
+}
+// segment offsets of the sorted, compacted slots: seg_off[a] = first sorted slot of account a (counts then scan)
+__global__ void count_per_account_kernel(const uint32_t* __restrict__ acc_sorted, uint32_t n, uint32_t* __restrict__ counts)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&counts[acc_sorted[i]], 1u);
+}
+// account leaf value rlp([nonce, balance, storage_root, code_hash]) in sorted account order
+__global__ void account_size_kernel(const uint64_t* __restrict__ nonce, const uint8_t* __restrict__ balance32,
+                                    const uint32_t* __restrict__ acc_of_sorted, uint32_t n, uint64_t* __restrict__ size)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t a = acc_of_sorted[i];
+        const uint64_t nn = nonce[a];
+        const uint32_t nl = be_len(nn);
+        uint64_t payload = (nl == 0) ? 1 : ((nl == 1 && nn < 0x80) ? 1 : 1 + nl);
+        const uint8_t* b = balance32 + 32ull * a;
+        uint32_t z = 0;
+        while (z < 32 && b[z] == 0) ++z;
+        const uint32_t bl = 32 - z;
+        payload += (bl == 0) ? 1 : ((bl == 1 && b[z] < 0x80) ? 1 : 1 + bl);
+        payload += 33 + 33;
+        size[i] = hdr_size(payload) + payload;
+    }
+}
+__global__ void account_fill_kernel(const uint64_t* __restrict__ nonce, const uint8_t* __restrict__ balance32,
+                                    const uint8_t* __restrict__ storage_roots, const uint8_t* __restrict__ code_hashes,
+                                    const uint8_t* __restrict__ addr_hashes, const uint32_t* __restrict__ acc_of_sorted, uint32_t n,
+                                    const uint64_t* __restrict__ val_off, uint8_t* __restrict__ keys_out, uint32_t* __restrict__ key_off,
+                                    uint8_t* __restrict__ vals_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+        key_off[i] = 32u * i;
+        if (i == n) break;
+        const uint32_t a = acc_of_sorted[i];
+        for (int b = 0; b < 32; ++b) keys_out[32ull * i + b] = addr_hashes[32ull * a + b];
+        uint8_t* out = vals_out + val_off[i];
+        const uint64_t total = val_off[i + 1] - val_off[i];
+        uint32_t hdr = 1;
+        for (uint32_t cand = 1; cand <= 3; ++cand)
+            if (hdr_size(total - cand) == cand) { hdr = cand; break; }
+        uint8_t* q = out + put_hdr(out, total - hdr, 0xc0, 0xf7);
+        const uint64_t nn = nonce[a];
+        const uint32_t nl = be_len(nn);
+        if (nl == 0) *q++ = 0x80;
+        else if (nl == 1 && nn < 0x80) *q++ = (uint8_t)nn;
+        else { *q++ = (uint8_t)(0x80 + nl); for (uint32_t b = 0; b < nl; ++b) *q++ = (uint8_t)(nn >> (8 * (nl - 1 - b))); }
+        const uint8_t* bal = balance32 + 32ull * a;
+        uint32_t z = 0;
+        while (z < 32 && bal[z] == 0) ++z;
+        const uint32_t bl = 32 - z;
+        if (bl == 0) *q++ = 0x80;
+        else if (bl == 1 && bal[z] < 0x80) *q++ = bal[z];
+        else { *q++ = (uint8_t)(0x80 + bl); for (uint32_t b = 0; b < bl; ++b) *q++ = bal[z + b]; }
+        *q++ = 0xa0;
+        for (int b = 0; b < 32; ++b) *q++ = storage_roots[32ull * a + b];
+        *q++ = 0xa0;
+        for (int b = 0; b < 32; ++b) *q++ = code_hashes[32ull * a + b];
+    }
+}
+__global__ void gather_rows32_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t cnt, uint8_t* __restrict__ dst)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint4* p = reinterpret_cast<const uint4*>(src + 32ull * idx[i]);
+        uint4* q = reinterpret_cast<uint4*>(dst + 32ull * i);
+        q[0] = p[0];
+        q[1] = p[1];
+    }
+}
+__global__ void fixed_offsets_kernel(uint64_t* off, uint64_t n, uint64_t stride)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) off[i] = stride * i;
+}
+
+} // namespace
+
+// stable LSD radix sort of n items by (segment, 32-byte big-endian hash): perm_out[i] = index of the i-th smallest
+int phant_gpu_ctx::sort_by_segment_and_hash(const uint8_t* d_hashes, const uint32_t* d_seg /*nullable*/, uint32_t n, uint32_t* d_perm_out,
+                                            DevBuf& scratch)
+{
+    phant_gpu_ctx* ctx = this;
+    cudaStream_t s = stream;
+    if (n == 0) return PHANT_GPU_OK;
+    RC(scratch.reserve(ctx, 8ull * n * 2 + 4ull * n * 3 + 64));
+    uint64_t* kin = (uint64_t*)scratch.ptr;
+    uint64_t* kout = kin + n;
+    uint32_t* pa = (uint32_t*)(kout + n);
+    uint32_t* pb = pa + n;
+    uint32_t* sk = pb + n;
+    iota_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(pa, n);
+    size_t temp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint64_t*)kin, kout, (const uint32_t*)pa, pb, (int64_t)n, 0, 64, s));
+    RC(d_cub.reserve(ctx, temp));
+    uint32_t* cur = pa;
+    uint32_t* nxt = pb;
+    for (int w = 3; w >= 0; --w) { // least significant word first
+        key_word_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(d_hashes, cur, n, (uint32_t)w, kin);
+        CU(cub::DeviceRadixSort::SortPairs(d_cub.ptr, temp, (const uint64_t*)kin, kout, (const uint32_t*)cur, nxt, (int64_t)n, 0, 64, s));
+        uint32_t* tsw = cur; cur = nxt; nxt = tsw;
+        stats.launches += 2;
+    }
+    if (d_seg) {
+        gather_u32_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(d_seg, cur, n, sk);
+        size_t temp2 = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, temp2, (const uint32_t*)sk, (uint32_t*)kout, (const uint32_t*)cur, nxt, (int64_t)n, 0, 32, s));
+        RC(d_cub.reserve(ctx, temp2));
+        // d_cub may have moved: temp storage is only used inside each call, so this is safe
+        CU(cub::DeviceRadixSort::SortPairs(d_cub.ptr, temp2, (const uint32_t*)sk, (uint32_t*)kout, (const uint32_t*)cur, nxt, (int64_t)n, 0, 32, s));
+        uint32_t* tsw = cur; cur = nxt; nxt = tsw;
+        stats.launches += 2;
+    }
+    CU(cudaMemcpyAsync(d_perm_out, cur, 4ull * n, cudaMemcpyDeviceToDevice, s));
+    return PHANT_GPU_OK;
+}
+
+extern "C" int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts* a, uint8_t out_root[32])
+{
+    if (!ctx || !a || !out_root) return PHANT_GPU_E_INVALID;
+    if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) return PHANT_GPU_E_INVALID; // S takes host tables (it is the StateDB flattening)
+    const uint64_t n = a->n_accounts;
+    static const uint8_t EMPTY[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                      0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+    if (n == 0) { memcpy(out_root, EMPTY, 32); return PHANT_GPU_OK; }
+    if (n >= (1ull << 30) || !a->addr20 || !a->nonce || !a->balance32 || !a->code_off || !a->slot_off) return PHANT_GPU_E_INVALID;
+    for (uint64_t i = 0; i < n; ++i)
+        if (a->code_off[i + 1] < a->code_off[i] || a->slot_off[i + 1] < a->slot_off[i]) return PHANT_GPU_E_INVALID;
+    const uint64_t code_bytes = a->code_off[n] - a->code_off[0], n_slots = a->slot_off[n] - a->slot_off[0];
+    if (a->code_off[0] != 0 || a->slot_off[0] != 0) return PHANT_GPU_E_INVALID;
+    if ((code_bytes && !a->code) || (n_slots && (!a->slot_keys32 || !a->slot_vals32)) || n_slots >= (1ull << 30)) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int dev = ctx->device;
+
+    // ---- stage the tables (one arena in st_in) ----
+    auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
+    const uint64_t o_addr = 0, o_nonce = up(o_addr + 20 * n), o_bal = up(o_nonce + 8 * n), o_code = up(o_bal + 32 * n),
+                   o_coff = up(o_code + code_bytes + 64), o_skey = up(o_coff + 8 * (n + 1)), o_sval = up(o_skey + 32 * n_slots + 64),
+                   o_soff = up(o_sval + 32 * n_slots + 64), o_end = up(o_soff + 8 * (n + 1));
+    RC(ctx->st_in.reserve(ctx, o_end));
+    uint8_t* in = (uint8_t*)ctx->st_in.ptr;
+    CU(cudaMemcpyAsync(in + o_addr, a->addr20, 20 * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(in + o_nonce, a->nonce, 8 * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(in + o_bal, a->balance32, 32 * n, cudaMemcpyHostToDevice, s));
+    if (code_bytes) CU(cudaMemcpyAsync(in + o_code, a->code, code_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(in + o_coff, a->code_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    if (n_slots) {
+        CU(cudaMemcpyAsync(in + o_skey, a->slot_keys32, 32 * n_slots, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(in + o_sval, a->slot_vals32, 32 * n_slots, cudaMemcpyHostToDevice, s));
+    }
+    CU(cudaMemcpyAsync(in + o_soff, a->slot_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += 60 * n + code_bytes + 64 * n_slots + 16 * (n + 1);
+
+    // ---- hashes: keccak(addr), keccak(code), keccak(slot key) (batched Keccak kernel, three launches) ----
+    const uint64_t h_addr = 0, h_code = up(32 * n), h_slot = up(h_code + 32 * n), h_sroot = up(h_slot + 32 * n_slots + 32),
+                   h_offs = up(h_sroot + 32 * n), h_end = up(h_offs + 8 * ((n > n_slots ? n : n_slots) + 1));
+    RC(ctx->st_hash.reserve(ctx, h_end));
+    uint8_t* hb = (uint8_t*)ctx->st_hash.ptr;
+    uint64_t* fixed = (uint64_t*)(hb + h_offs);
+    fixed_offsets_kernel<<<grid1d(dev, n, 256), 256, 0, s>>>(fixed, n, 20);
+    ctx->stats.launches++;
+    RC(ctx->hash_csr(in + o_addr, fixed, n, 20 * n, hb + h_addr));
+    RC(ctx->hash_csr(in + o_code, (const uint64_t*)(in + o_coff), n, code_bytes, hb + h_code));
+    if (n_slots) {
+        fixed_offsets_kernel<<<grid1d(dev, n_slots, 256), 256, 0, s>>>(fixed, n_slots, 32);
+        ctx->stats.launches++;
+        RC(ctx->hash_csr(in + o_skey, fixed, n_slots, 32 * n_slots, hb + h_slot));
+    }
+
+    // ---- storage tries: drop zero slots, sort by (account, hashed key), build all tries as one forest ----
+    uint8_t* sroots = hb + h_sroot;
+    RC(ctx->st_seg.reserve(ctx, 4ull * (n + 2) * 2 + 4ull * (n_slots + 1) * 4 + (n_slots + 1) + 256));
+    uint32_t* seg_cnt = (uint32_t*)ctx->st_seg.ptr;
+    uint32_t* seg_off = seg_cnt + (n + 2);
+    uint32_t* acc_of_slot = seg_off + (n + 2);
+    uint32_t* kept = acc_of_slot + (n_slots + 1);   // compacted -> slot
+    uint32_t* perm = kept + (n_slots + 1);          // sorted -> compacted
+    uint32_t* slot_sorted = perm + (n_slots + 1);   // sorted -> slot
+    uint8_t* keep = (uint8_t*)(slot_sorted + (n_slots + 1));
+    uint32_t m = 0; // kept slots
+    if (n_slots) {
+        slot_flag_kernel<<<grid1d(dev, n_slots, 256), 256, 0, s>>>(in + o_sval, n_slots, keep);
+        slot_account_kernel<<<grid1d(dev, n, 256, 32), 256, 0, s>>>((const uint64_t*)(in + o_soff), (uint32_t)n, acc_of_slot);
+        iota_kernel<<<grid1d(dev, n_slots, 256), 256, 0, s>>>(perm, (uint32_t)n_slots);
+        ctx->stats.launches += 3;
+        RC(ctx->d_b3.reserve(ctx, 64));
+        size_t temp = 0;
+        CU(cub::DeviceSelect::Flagged(nullptr, temp, (const uint32_t*)perm, (const uint8_t*)keep, kept, (uint32_t*)ctx->d_b3.ptr, (int64_t)n_slots, s));
+        RC(ctx->d_cub.reserve(ctx, temp));
+        CU(cub::DeviceSelect::Flagged(ctx->d_cub.ptr, temp, (const uint32_t*)perm, (const uint8_t*)keep, kept, (uint32_t*)ctx->d_b3.ptr, (int64_t)n_slots, s));
+        CU(cudaMemcpyAsync(&m, ctx->d_b3.ptr, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    CU(cudaMemsetAsync(seg_cnt, 0, 4ull * (n + 2), s));
+    if (m) {
+        // gather the kept slots' hashes / accounts into compact arrays, sort, and lay the forest inputs out
+        RC(ctx->st_tmp.reserve(ctx, 32ull * m + 4ull * m * 2 + 64 + 32ull * m + 4ull * (m + 1) + 8ull * (m + 1) * 2 + 33ull * m + 256));
+        uint8_t* ch = (uint8_t*)ctx->st_tmp.ptr;               // compact hashes
+        uint32_t* cacc = (uint32_t*)(ch + 32ull * m);         // compact account ids
+        uint32_t* acc_sorted = cacc + m;
+        uint8_t* fk = (uint8_t*)(acc_sorted + m + 16);        // forest keys
+        uint32_t* fko = (uint32_t*)(fk + 32ull * m);
+        uint64_t* fvs = (uint64_t*)(((uintptr_t)(fko + (m + 1)) + 7) & ~(uintptr_t)7);
+        uint64_t* fvo = fvs + (m + 1);
+        uint8_t* fv = (uint8_t*)(fvo + (m + 1));
+        gather_rows32_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(hb + h_slot, kept, m, ch);
+        gather_u32_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(acc_of_slot, kept, m, cacc);
+        ctx->stats.launches += 2;
+        RC(ctx->sort_by_segment_and_hash(ch, cacc, m, perm, ctx->st_sort));
+        gather_u32_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(kept, perm, m, slot_sorted);
+        gather_u32_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(cacc, perm, m, acc_sorted);
+        count_per_account_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(acc_sorted, m, seg_cnt);
+        storage_value_size_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(in + o_sval, slot_sorted, m, fvs);
+        ctx->stats.launches += 4;
+        RC(scan_sizes(ctx, fvs, fvo, m));
+        storage_fill_kernel<<<grid1d(dev, m + 1, 256), 256, 0, s>>>(hb + h_slot, in + o_sval, slot_sorted, m, fvo, fk, fko, fv);
+        ctx->stats.launches++;
+        size_t temp = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, temp, (const uint32_t*)seg_cnt, seg_off, (int64_t)(n + 1), s));
+        RC(ctx->d_cub.reserve(ctx, temp));
+        CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.ptr, temp, (const uint32_t*)seg_cnt, seg_off, (int64_t)(n + 1), s));
+        RC(ctx->build_forest(fk, fko, fv, fvo, m, seg_off, (uint32_t)n, acc_sorted, sroots));
+    } else {
+        CU(cudaMemsetAsync(seg_off, 0, 4ull * (n + 2), s));
+        RC(ctx->build_forest(nullptr, seg_off, nullptr, nullptr, 0, seg_off, (uint32_t)n, nullptr, sroots)); // every storage trie empty
+    }
+
+    // ---- account trie ----
+    RC(ctx->st_acc.reserve(ctx, 4ull * n + 32ull * n + 4ull * (n + 1) + 8ull * (n + 1) * 2 + 112ull * n + 256));
+    uint32_t* acc_perm = (uint32_t*)ctx->st_acc.ptr;
+    uint8_t* ak = (uint8_t*)(acc_perm + n + (n & 1));
+    uint32_t* ako = (uint32_t*)(ak + 32ull * n);
+    uint64_t* avs = (uint64_t*)(((uintptr_t)(ako + (n + 1)) + 7) & ~(uintptr_t)7);
+    uint64_t* avo = avs + (n + 1);
+    uint8_t* av = (uint8_t*)(avo + (n + 1));
+    RC(ctx->sort_by_segment_and_hash(hb + h_addr, nullptr, (uint32_t)n, acc_perm, ctx->st_sort));
+    account_size_kernel<<<grid1d(dev, n, 256), 256, 0, s>>>((const uint64_t*)(in + o_nonce), in + o_bal, acc_perm, (uint32_t)n, avs);
+    ctx->stats.launches++;
+    RC(scan_sizes(ctx, avs, avo, n));
+    account_fill_kernel<<<grid1d(dev, n + 1, 256), 256, 0, s>>>((const uint64_t*)(in + o_nonce), in + o_bal, sroots, hb + h_code, hb + h_addr, acc_perm,
+                                                               (uint32_t)n, avo, ak, ako, av);
+    ctx->stats.launches++;
+    uint32_t seg[2] = {0, (uint32_t)n};
+    RC(ctx->d_first.reserve(ctx, 64));
+    CU(cudaMemcpyAsync(ctx->d_first.ptr, seg, 8, cudaMemcpyHostToDevice, s));
+    RC(ctx->d_roots.reserve(ctx, 32));
+    RC(ctx->build_forest(ak, ako, av, avo, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr));
+    CU(cudaMemcpyAsync(out_root, ctx->d_roots.ptr, 32, cudaMemcpyDeviceToHost, s));
+    ctx->stats.d2h_bytes += 32;
+    CU(cudaStreamSynchronize(s));
+    return PHANT_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// U: resident complete trie
+// ------------------------------------------------------------------------------------------------
+struct phant_gpu_trie {
+    phant_gpu_ctx* ctx;
+    uint32_t depth;
+    std::vector<uint8_t*> level; // level[l] = 16^l hashes
+    DevBuf store, work;
+};
+
+namespace {
+
+__device__ __forceinline__ uint64_t sm64(uint64_t& s)
+{
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void ctrie_fill_leaves_kernel(uint64_t seed, uint64_t n_leaves, uint8_t* __restrict__ out)
+{
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_leaves; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = seed ^ (0xC4ull * 0xA24BAED4963EE407ull) ^ (j * 0xD1342543DE82EF95ull);
+        (void)sm64(s);
+        uint64_t* o = reinterpret_cast<uint64_t*>(out + 32 * j);
+        for (int w = 0; w < 4; ++w) o[w] = sm64(s); // little-endian bytes == the oracle's byte order
+    }
+}
+// branch node over 16 resident child hashes: f9 0211 | 16 x (a0 hash) | 80  (mpt.zig:218-247), 532 bytes, written to the arena
+// parents: list of parent positions (nullable = identity).  16 threads per parent, 33 bytes each.
+__global__ void ctrie_branch_encode_kernel(const uint8_t* __restrict__ child_level, const uint32_t* __restrict__ parents, uint64_t cnt,
+                                           uint8_t* __restrict__ arena)
+{
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t v = threadIdx.x & 15;
+    for (uint64_t u = gid >> 4; u < cnt; u += ((uint64_t)gridDim.x * blockDim.x) >> 4) {
+        const uint64_t p = parents ? parents[u] : u;
+        uint8_t* out = arena + 532 * u;
+        if (v == 0) { out[0] = 0xf9; out[1] = 0x02; out[2] = 0x11; out[531] = 0x80; }
+        const uint4* h = reinterpret_cast<const uint4*>(child_level + 32 * (16 * p + v));
+        const uint4 a = h[0], b = h[1];
+        uint8_t* q = out + 3 + 33 * v;
+        q[0] = 0xa0;
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            q[1 + 4 * i] = (uint8_t)w[i]; q[2 + 4 * i] = (uint8_t)(w[i] >> 8);
+            q[3 + 4 * i] = (uint8_t)(w[i] >> 16); q[4 + 4 * i] = (uint8_t)(w[i] >> 24);
+        }
+    }
+}
+__global__ void ctrie_scatter_kernel(const uint8_t* __restrict__ digests, const uint32_t* __restrict__ pos, uint64_t cnt, uint8_t* __restrict__ level)
+{
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < cnt; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4* p = reinterpret_cast<const uint4*>(digests + 32 * u);
+        uint4* q = reinterpret_cast<uint4*>(level + 32ull * (pos ? pos[u] : u));
+        q[0] = p[0];
+        q[1] = p[1];
+    }
+}
+// dirty leaves: position = first `depth` nibbles of the key; leaf RLP = list[hp(nibbles[depth..64), leaf), value]
+__global__ void ctrie_leaf_pos_kernel(const uint8_t* __restrict__ keys32, uint64_t n, uint32_t depth, uint32_t* __restrict__ pos)
+{
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t* key = keys32 + 32 * k;
+        uint32_t p = 0;
+        for (uint32_t i = 0; i < depth; ++i) p = p * 16 + ((i & 1) ? (key[i >> 1] & 15u) : (key[i >> 1] >> 4));
+        pos[k] = p;
+    }
+}
+__global__ void ctrie_leaf_size_kernel(const uint8_t* __restrict__ vals, const uint32_t* __restrict__ val_off, uint64_t n, uint32_t depth,
+                                       uint64_t* __restrict__ size)
+{
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t cnt = 64 - depth, hpn = 1 + cnt / 2;
+        const uint64_t vl = val_off[k + 1] - val_off[k];
+        // the first hex-prefix byte is 0x20 or 0x3n: a lone byte < 0x80 encodes as itself
+        const uint64_t payload = (hpn == 1 ? 1 : 1 + hpn) + str_size(vl, vl ? vals[val_off[k]] : 0);
+        size[k] = hdr_size(payload) + payload;
+    }
+}
+__global__ void ctrie_leaf_encode_kernel(const uint8_t* __restrict__ keys32, const uint8_t* __restrict__ vals, const uint32_t* __restrict__ val_off,
+                                         uint64_t n, uint32_t depth, const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena)
+{
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t* key = keys32 + 32 * k;
+        const uint32_t cnt = 64 - depth, hpn = 1 + cnt / 2;
+        const uint64_t vl = val_off[k + 1] - val_off[k];
+        const uint8_t* v = vals + val_off[k];
+        const uint64_t s_hp = hpn == 1 ? 1 : 1 + hpn, s_v = str_size(vl, vl ? v[0] : 0);
+        uint8_t* out = arena + aoff[k];
+        uint8_t* q = out + put_hdr(out, s_hp + s_v, 0xc0, 0xf7);
+        if (hpn > 1) *q++ = (uint8_t)(0x80 + hpn);
+        uint32_t i = depth;
+#define KN(j) (((j) & 1) ? (key[(j) >> 1] & 15u) : (key[(j) >> 1] >> 4))
+        if (cnt & 1) { *q++ = (uint8_t)(0x30 | KN(i)); ++i; } else *q++ = 0x20;
+        for (; i < 64; i += 2) *q++ = (uint8_t)((KN(i) << 4) | KN(i + 1));
+#undef KN
+        if (s_v > vl) q += put_hdr(q, vl, 0x80, 0xb7);
+        for (uint64_t b = 0; b < vl; ++b) q[b] = v[b];
+    }
+}
+__global__ void shift4_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out)
+{
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) out[k] = in[k] >> 4;
+}
+
+int ctrie_hash_level(phant_gpu_trie* t, uint32_t l, const uint32_t* d_parents, uint64_t cnt)
+{
+    // re-hash `cnt` branch nodes of level l (positions d_parents) from level l+1
+    phant_gpu_ctx* ctx = t->ctx;
+    cudaStream_t s = ctx->stream;
+    const uint64_t batch = 1ull << 20; // bound the scratch arena (532 B per node)
+    for (uint64_t b0 = 0; b0 < cnt; b0 += batch) {
+        const uint64_t c = cnt - b0 < batch ? cnt - b0 : batch;
+        RC(t->work.reserve(ctx, 532 * c + 64 + 8 * (c + 2) + 32 * c + 256));
+        uint8_t* arena = (uint8_t*)t->work.ptr;
+        uint64_t* offs = (uint64_t*)(arena + ((532 * c + 64 + 15) & ~15ull));
+        uint8_t* dg = (uint8_t*)(offs + ((c + 2) & ~1ull)); // 16-byte aligned: digests are stored as 128-bit words
+        const uint32_t* par = d_parents + b0;
+        fixed_offsets_kernel<<<grid1d(ctx->device, c, 256), 256, 0, s>>>(offs, c, 532);
+        ctrie_branch_encode_kernel<<<grid1d(ctx->device, c, 128, 16), 128, 0, s>>>(t->level[l + 1], par, c, arena);
+        ctx->stats.launches += 2;
+        const uint32_t saved = ctx->flags;
+        ctx->flags |= PHANT_GPU_FLAG_NO_BINNING; // all 532-byte messages: nothing to regroup
+        const int rc = ctx->hash_csr(arena, offs, c, 532 * c, dg);
+        ctx->flags = saved;
+        RC(rc);
+        ctrie_scatter_kernel<<<grid1d(ctx->device, c, 256), 256, 0, s>>>(dg, par, c, t->level[l]);
+        ctx->stats.launches++;
+    }
+    CU(cudaGetLastError());
+    return PHANT_GPU_OK;
+}
+
+} // namespace
+
+extern "C" int phant_gpu_trie_open(phant_gpu_ctx* ctx, const phant_gpu_trie_desc* desc, phant_gpu_trie** out)
+{
+    if (!ctx || !desc || !out) return PHANT_GPU_E_INVALID;
+    *out = nullptr;
+    if (desc->kind != 0 || desc->depth < 1 || desc->depth > 7) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    phant_gpu_trie* t = new (std::nothrow) phant_gpu_trie();
+    if (!t) return PHANT_GPU_E_OOM;
+    t->ctx = ctx;
+    t->depth = desc->depth;
+    uint64_t total = 0, cnt = 1;
+    std::vector<uint64_t> offs;
+    for (uint32_t l = 0; l <= desc->depth; ++l) { offs.push_back(total); total += 32 * cnt; cnt *= 16; }
+    if (int rc = t->store.reserve(ctx, total)) { delete t; return rc; }
+    for (uint32_t l = 0; l <= desc->depth; ++l) t->level.push_back((uint8_t*)t->store.ptr + offs[l]);
+    const uint64_t n_leaves = cnt / 16;
+    ctrie_fill_leaves_kernel<<<grid1d(ctx->device, n_leaves, 256), 256, 0, ctx->stream>>>(desc->seed, n_leaves, t->level[desc->depth]);
+    ctx->stats.launches++;
+    // all branch levels bottom-up; explicit parent lists keep the batches simple
+    for (int l = (int)desc->depth - 1; l >= 0; --l) {
+        uint64_t n_l = 1;
+        for (int k = 0; k < l; ++k) n_l *= 16;
+        DevBuf ids;
+        if (int rc = ids.reserve(ctx, 4 * n_l + 16)) { t->store.release(); delete t; return rc; }
+        iota_kernel<<<grid1d(ctx->device, n_l, 256), 256, 0, ctx->stream>>>((uint32_t*)ids.ptr, (uint32_t)n_l);
+        int rc = ctrie_hash_level(t, (uint32_t)l, (const uint32_t*)ids.ptr, n_l);
+        cudaStreamSynchronize(ctx->stream);
+        ids.release();
+        if (rc) { t->store.release(); t->work.release(); delete t; return rc; }
+    }
+    *out = t;
+    return PHANT_GPU_OK;
+}
+
+extern "C" int phant_gpu_trie_root(phant_gpu_trie* t, uint8_t out_root[32])
+{
+    if (!t || !out_root) return PHANT_GPU_E_INVALID;
+    phant_gpu_ctx* ctx = t->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(out_root, t->level[0], 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHANT_GPU_OK;
+}
+
+extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* leaf_vals, const uint32_t* val_off,
+                                     uint64_t n_dirty, uint8_t out_root[32])
+{
+    if (!t || !out_root) return PHANT_GPU_E_INVALID;
+    phant_gpu_ctx* ctx = t->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (n_dirty == 0) return phant_gpu_trie_root(t, out_root);
+    if (!keys32 || !val_off || n_dirty >= (1ull << 28)) return PHANT_GPU_E_INVALID;
+    const uint8_t* d_keys = keys32; const uint8_t* d_vals = leaf_vals; const uint32_t* d_voff = val_off;
+    uint64_t vb = 0;
+    if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS)) {
+        for (uint64_t i = 0; i < n_dirty; ++i) if (val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
+        vb = val_off[n_dirty];
+        if (vb && !leaf_vals) return PHANT_GPU_E_INVALID;
+        RC(ctx->d_msgs.reserve(ctx, 32 * n_dirty + vb + 4 * (n_dirty + 1) + 256));
+        uint8_t* dk = (uint8_t*)ctx->d_msgs.ptr;
+        uint8_t* dv = dk + 32 * n_dirty;
+        uint32_t* dvo = (uint32_t*)(dv + ((vb + 63) & ~63ull));
+        CU(cudaMemcpyAsync(dk, keys32, 32 * n_dirty, cudaMemcpyHostToDevice, s));
+        if (vb) CU(cudaMemcpyAsync(dv, leaf_vals, vb, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dvo, val_off, 4 * (n_dirty + 1), cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += 32 * n_dirty + vb + 4 * (n_dirty + 1);
+        d_keys = dk; d_vals = dv; d_voff = dvo;
+    } else {
+        CU(cudaMemcpyAsync(&vb, val_off + n_dirty, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    const uint32_t L = t->depth;
+    // ---- dirty leaves: encode, hash (batched Keccak), scatter into the leaf level ----
+    RC(ctx->d_b0.reserve(ctx, 4 * n_dirty * 4 + 8 * (n_dirty + 2) * 2 + 32 * n_dirty + 256));
+    uint32_t* pos = (uint32_t*)ctx->d_b0.ptr;
+    uint32_t* pa = pos + n_dirty;
+    uint32_t* pb = pa + n_dirty;
+    uint32_t* pc = pb + n_dirty;
+    uint64_t* sizes = (uint64_t*)(((uintptr_t)(pc + n_dirty) + 15) & ~(uintptr_t)15);
+    uint64_t* offs = sizes + ((n_dirty + 2) & ~1ull);
+    uint8_t* dg = (uint8_t*)(offs + ((n_dirty + 2) & ~1ull)); // 16-byte aligned
+    ctrie_leaf_pos_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(d_keys, n_dirty, L, pos);
+    ctrie_leaf_size_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(d_vals, d_voff, n_dirty, L, sizes);
+    RC(scan_sizes(ctx, sizes, offs, n_dirty));
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, offs + n_dirty, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    RC(ctx->d_b1.reserve(ctx, total + 64));
+    ctrie_leaf_encode_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(d_keys, d_vals, d_voff, n_dirty, L, offs, (uint8_t*)ctx->d_b1.ptr);
+    ctx->stats.launches += 3;
+    RC(ctx->hash_csr((const uint8_t*)ctx->d_b1.ptr, offs, n_dirty, total, dg));
+    ctrie_scatter_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(dg, pos, n_dirty, t->level[L]);
+    ctx->stats.launches++;
+    // ---- frontier: unique parents level by level (sort once, then shift + unique) ----
+    size_t temp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, temp, (const uint32_t*)pos, pa, (int64_t)n_dirty, 0, 4 * (int)L, s));
+    RC(ctx->d_cub.reserve(ctx, temp));
+    CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub.ptr, temp, (const uint32_t*)pos, pa, (int64_t)n_dirty, 0, 4 * (int)L, s));
+    RC(ctx->d_b3.reserve(ctx, 64));
+    uint64_t cnt = n_dirty;
+    uint32_t* cur = pa;
+    uint32_t* tmp = pb;
+    uint32_t* uniq = pc;
+    for (int l = (int)L - 1; l >= 0; --l) {
+        shift4_kernel<<<grid1d(ctx->device, cnt, 256), 256, 0, s>>>(cur, cnt, tmp);
+        size_t t2 = 0;
+        CU(cub::DeviceSelect::Unique(nullptr, t2, (const uint32_t*)tmp, uniq, (uint32_t*)ctx->d_b3.ptr, (int64_t)cnt, s));
+        RC(ctx->d_cub.reserve(ctx, t2));
+        CU(cub::DeviceSelect::Unique(ctx->d_cub.ptr, t2, (const uint32_t*)tmp, uniq, (uint32_t*)ctx->d_b3.ptr, (int64_t)cnt, s));
+        uint32_t nu = 0;
+        CU(cudaMemcpyAsync(&nu, ctx->d_b3.ptr, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        ctx->stats.launches += 2;
+        cnt = nu;
+        RC(ctrie_hash_level(t, (uint32_t)l, uniq, cnt));
+        uint32_t* x = cur; cur = uniq; uniq = x; // the unique parents are the next level's (sorted) children
+    }
+    CU(cudaMemcpyAsync(out_root, t->level[0], 32, cudaMemcpyDeviceToHost, s));
+    ctx->stats.d2h_bytes += 32;
+    CU(cudaStreamSynchronize(s));
+    return PHANT_GPU_OK;
+}
+
+extern "C" void phant_gpu_trie_close(phant_gpu_trie* t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    t->store.release();
+    t->work.release();
+    delete t;
+}

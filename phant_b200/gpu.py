@@ -121,6 +121,8 @@ class Context:
         self.flags = flags
 
     def close(self):
+        for t in list(getattr(self, "_tries", [])):
+            t.close()
         if getattr(self, "_h", None):
             _lib().phant_gpu_destroy(self._h)
             self._h = None
@@ -197,6 +199,9 @@ class ResidentTrie:
         self._h = C.c_void_p()
         d = TrieDesc(kind, depth, seed)
         ctx._chk(_lib().phant_gpu_trie_open(ctx._h, C.byref(d), C.byref(self._h)), "trie_open")
+        if not hasattr(ctx, "_tries"):
+            ctx._tries = []
+        ctx._tries.append(self)
 
     def root(self):
         out = np.zeros(32, np.uint8)
@@ -210,9 +215,11 @@ class ResidentTrie:
         return out.tobytes()
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             _lib().phant_gpu_trie_close(self._h)
-            self._h = None
+        self._h = None
+        if self in getattr(self.ctx, "_tries", []):
+            self.ctx._tries.remove(self)
 
     __del__ = close
 
