@@ -173,8 +173,10 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = gpu.Context(local_rank)
+    from phant_b200 import shard
     n = PROOFS_PER_GPU
-    first_index = rank * n
+    first_index, hi = shard.shard_range(world * n, rank, world)  # contiguous, 64-aligned proof ranges (weak scaling)
+    assert hi - first_index == n
 
     # ---- witnesses generated in HBM (setup, untimed) ----
     n_nodes, n_bytes = ctx.synth_sizes(2, n, depth=DEPTH, first=first_index)

@@ -1,0 +1,245 @@
+// phant_host.hpp -- C++ host mirror of the phant functions that sit on the hot path, over the C ABI of
+// include/phant_gpu.h.  phant's own host code is Zig; this image has no Zig toolchain, so the mirror is
+// C++ (the reference is compiled code) with the same names, argument meaning and error behaviour:
+//
+//   hasher::keccak256 / keccak256WithPrefix      src/crypto/hasher.zig:4-17
+//   mpt::KeyVal{init,lessThan}, mpt::mptize       src/mpt/mpt.zig:13-45
+//   blockchain::calculateMPTRoot                  src/blockchain/blockchain.zig:209-235
+//   engine_api::payloadListRoot                   src/engine_api/execution_payload.zig:125-139 (32-byte BE index keys)
+//   state::StateDB::root                          hook src/blockchain/blockchain.zig:83-85 (missing in the reference)
+//   engine_api::verifyWitness                     hook src/engine_api/execution_payload.zig:177-178 (TODO in the reference)
+//
+// No arithmetic happens here: every hash and every root comes from libphantgpu.so.  Errors from the library
+// surface as phant::GpuError (the Zig binding maps them to error.GpuBackend).
+#pragma once
+#include "../include/phant_gpu.h"
+
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace phant {
+
+using Hash32 = std::array<uint8_t, 32>;
+using Address = std::array<uint8_t, 20>;
+using Bytes = std::vector<uint8_t>;
+
+struct GpuError : std::runtime_error {
+    int code;
+    GpuError(int c, const std::string& where) : std::runtime_error(where + ": " + phant_gpu_strerror(c)), code(c) {}
+};
+
+// One device, one stream.  Not re-entrant: one per host thread (src/main.zig:143-149 runs handlers on worker threads).
+class Gpu {
+public:
+    explicit Gpu(int device = 0)
+    {
+        if (phant_gpu_abi_version() != PHANT_GPU_ABI_VERSION) throw GpuError(PHANT_GPU_E_INVALID, "abi version");
+        phant_gpu_config cfg{};
+        cfg.device = device;
+        const int rc = phant_gpu_create(&ctx_, &cfg);
+        if (rc != 0) throw GpuError(rc, "phant_gpu_create"); // no device: the caller keeps its CPU path; nothing is emulated here
+    }
+    ~Gpu() { phant_gpu_destroy(ctx_); }
+    Gpu(const Gpu&) = delete;
+    Gpu& operator=(const Gpu&) = delete;
+    phant_gpu_ctx* ctx() { return ctx_; }
+    void check(int rc, const char* where) const
+    {
+        if (rc != 0) throw GpuError(rc, std::string(where) + " [" + phant_gpu_last_error(ctx_) + "]");
+    }
+
+private:
+    phant_gpu_ctx* ctx_ = nullptr;
+};
+
+namespace hasher {
+// many inputs at once (the shape the GPU wants); msgs[i] are independent byte strings
+inline std::vector<Hash32> keccak256_batch(Gpu& g, const std::vector<Bytes>& msgs)
+{
+    Bytes flat;
+    std::vector<uint64_t> off(msgs.size() + 1, 0);
+    for (size_t i = 0; i < msgs.size(); ++i) {
+        flat.insert(flat.end(), msgs[i].begin(), msgs[i].end());
+        off[i + 1] = flat.size();
+    }
+    std::vector<Hash32> out(msgs.size());
+    if (!msgs.empty())
+        g.check(phant_gpu_keccak256_batch(g.ctx(), flat.data(), off.data(), msgs.size(), out[0].data()), "keccak256_batch");
+    return out;
+}
+inline Hash32 keccak256(Gpu& g, const Bytes& data) { return keccak256_batch(g, {data})[0]; }
+inline Hash32 keccak256WithPrefix(Gpu& g, const Bytes& prefix, const Bytes& data)
+{
+    Bytes m(prefix);
+    m.insert(m.end(), data.begin(), data.end());
+    return keccak256(g, m);
+}
+} // namespace hasher
+
+namespace mpt {
+inline const Hash32 empty_mpt_root = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                      0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+
+// mpt.zig:13-34
+struct KeyVal {
+    Bytes nibbles;
+    Bytes value;
+    static KeyVal init(const Bytes& key, const Bytes& value)
+    {
+        KeyVal kv;
+        kv.nibbles.reserve(2 * key.size());
+        for (uint8_t b : key) { kv.nibbles.push_back(b >> 4); kv.nibbles.push_back(b & 0x0f); }
+        kv.value = value;
+        return kv;
+    }
+    static bool lessThan(const KeyVal& a, const KeyVal& b) { return a.nibbles < b.nibbles; } // std::mem.lessThan on the nibbles
+};
+
+// mpt.zig:38-45: `list` must be sorted by key (the reference asserts); unsorted input -> GpuError(E_INVALID)
+inline Hash32 mptize(Gpu& g, const std::vector<KeyVal>& list)
+{
+    Bytes keys, vals;
+    std::vector<uint32_t> koff(list.size() + 1, 0);
+    std::vector<uint64_t> voff(list.size() + 1, 0);
+    for (size_t i = 0; i < list.size(); ++i) {
+        const Bytes& nb = list[i].nibbles;
+        if (nb.size() % 2) throw GpuError(PHANT_GPU_E_INVALID, "mptize: odd nibble count"); // KeyVal.init always makes pairs
+        for (size_t j = 0; j < nb.size(); j += 2) keys.push_back((uint8_t)((nb[j] << 4) | nb[j + 1]));
+        koff[i + 1] = (uint32_t)keys.size();
+        vals.insert(vals.end(), list[i].value.begin(), list[i].value.end());
+        voff[i + 1] = vals.size();
+    }
+    Hash32 root;
+    g.check(phant_gpu_mpt_root(g.ctx(), keys.data(), koff.data(), vals.data(), voff.data(), list.size(), root.data()), "mptize");
+    return root;
+}
+} // namespace mpt
+
+namespace rlp {
+inline Bytes encode_uint(uint64_t v)
+{
+    if (v == 0) return {0x80};
+    Bytes be;
+    for (int s = 56; s >= 0; s -= 8)
+        if (!be.empty() || (v >> s) & 0xff) be.push_back((uint8_t)(v >> s));
+    if (be.size() == 1 && be[0] < 0x80) return be;
+    Bytes out{(uint8_t)(0x80 + be.size())};
+    out.insert(out.end(), be.begin(), be.end());
+    return out;
+}
+} // namespace rlp
+
+namespace blockchain {
+// blockchain.zig:209-235: index trie of already-encoded items, keys rlp(i) visited in sorted order
+// (1..0x7f, then 0 as 0x80, then 0x80.. as 0x81 xx ..)
+inline Hash32 calculateMPTRoot(Gpu& g, const std::vector<Bytes>& encoded_items)
+{
+    std::vector<mpt::KeyVal> keyvals;
+    keyvals.reserve(encoded_items.size());
+    size_t i = 0;
+    for (; i + 1 < encoded_items.size() && i + 1 != 0x80; ++i)
+        keyvals.push_back(mpt::KeyVal::init({(uint8_t)(i + 1)}, encoded_items[i + 1]));
+    if (!encoded_items.empty()) {
+        keyvals.push_back(mpt::KeyVal::init({0x80}, encoded_items[0]));
+        ++i;
+    }
+    for (; i < encoded_items.size(); ++i) keyvals.push_back(mpt::KeyVal::init(rlp::encode_uint(i), encoded_items[i]));
+    return mpt::mptize(g, keyvals);
+}
+} // namespace blockchain
+
+namespace state {
+struct AccountState { // src/state/types.zig:13-33
+    uint64_t nonce = 0;
+    std::array<uint8_t, 32> balance{}; // u256, big endian
+    Bytes code;
+    std::map<std::array<uint8_t, 32>, std::array<uint8_t, 32>> storage; // slot -> value (zero values are deleted, statedb.zig:112-119)
+};
+
+class StateDB { // src/state/statedb.zig:16-30, plus the missing root()
+public:
+    std::map<Address, AccountState> db;
+
+    // the body of the check commented out at src/blockchain/blockchain.zig:83-85
+    Hash32 root(Gpu& g) const
+    {
+        const size_t n = db.size();
+        Bytes addr, bal, code, skeys, svals;
+        std::vector<uint64_t> nonce, coff{0}, soff{0};
+        for (const auto& [a, acc] : db) {
+            addr.insert(addr.end(), a.begin(), a.end());
+            nonce.push_back(acc.nonce);
+            bal.insert(bal.end(), acc.balance.begin(), acc.balance.end());
+            code.insert(code.end(), acc.code.begin(), acc.code.end());
+            coff.push_back(code.size());
+            for (const auto& [k, v] : acc.storage) {
+                skeys.insert(skeys.end(), k.begin(), k.end());
+                svals.insert(svals.end(), v.begin(), v.end());
+            }
+            soff.push_back(skeys.size() / 32);
+        }
+        phant_gpu_accounts t{};
+        t.n_accounts = n;
+        t.addr20 = addr.data(); t.nonce = nonce.data(); t.balance32 = bal.data();
+        t.code = code.data(); t.code_off = coff.data();
+        t.slot_keys32 = skeys.data(); t.slot_vals32 = svals.data(); t.slot_off = soff.data();
+        Hash32 r;
+        g.check(phant_gpu_state_root(g.ctx(), &t, r.data()), "StateDB.root");
+        return r;
+    }
+};
+} // namespace state
+
+namespace engine_api {
+// execution_payload.zig:125-139: index trie keyed by the 32-byte big-endian index (phant's non-standard keys)
+inline Hash32 payloadListRoot(Gpu& g, const std::vector<Bytes>& encoded_items)
+{
+    std::vector<mpt::KeyVal> kv;
+    for (size_t i = 0; i < encoded_items.size(); ++i) {
+        Bytes key(32, 0);
+        for (int b = 0; b < 8; ++b) key[31 - b] = (uint8_t)((uint64_t)i >> (8 * b));
+        kv.push_back(mpt::KeyVal::init(key, encoded_items[i]));
+    }
+    return mpt::mptize(g, kv); // big-endian fixed-width indices are already in sorted order
+}
+
+struct Witness {                       // flattened execution witness: one chain of nodes per key, root first
+    Bytes nodes;
+    std::vector<uint64_t> node_off{0};
+    std::vector<uint64_t> proof_first{0};
+    Bytes keys32;                      // hashed keys, 32 bytes each
+    void add_proof(const std::vector<Bytes>& chain, const Hash32& hashed_key)
+    {
+        for (const Bytes& n : chain) { nodes.insert(nodes.end(), n.begin(), n.end()); node_off.push_back(nodes.size()); }
+        proof_first.push_back(node_off.size() - 1);
+        keys32.insert(keys32.end(), hashed_key.begin(), hashed_key.end());
+    }
+};
+enum class ProofStatus : uint8_t { reject = 0, present = 1, absent = 2 };
+
+// the TODO at execution_payload.zig:177-178: every proof of the witness must verify against `state_root`;
+// returns per-proof status, throws only on backend errors (accept/reject is data)
+inline std::vector<ProofStatus> verifyWitness(Gpu& g, const Hash32& state_root, const Witness& w)
+{
+    const uint64_t n = w.proof_first.size() - 1;
+    std::vector<uint8_t> status(n);
+    std::vector<uint64_t> bitmap((n + 63) / 64);
+    phant_gpu_proof_batch b{};
+    b.n_proofs = n;
+    b.nodes = w.nodes.data(); b.node_off = w.node_off.data(); b.proof_first = w.proof_first.data();
+    b.keys32 = w.keys32.data(); b.roots32 = state_root.data(); b.n_roots = 1;
+    if (n) g.check(phant_gpu_verify_proofs(g.ctx(), &b, bitmap.data(), status.data(), nullptr, nullptr), "verifyWitness");
+    std::vector<ProofStatus> out(n);
+    for (uint64_t i = 0; i < n; ++i) out[i] = (ProofStatus)status[i];
+    return out;
+}
+} // namespace engine_api
+
+} // namespace phant

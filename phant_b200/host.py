@@ -1,0 +1,139 @@
+"""Python host mirror of the reference functions on the hot path (names follow the Zig sources), over the
+C ABI.  No arithmetic here -- flattening to CSR and one library call each.
+
+  keccak256 / keccak256_with_prefix   src/crypto/hasher.zig:4-17
+  KeyVal, mptize                      src/mpt/mpt.zig:13-45
+  calculate_mpt_root                  src/blockchain/blockchain.zig:209-235
+  payload_list_root                   src/engine_api/execution_payload.zig:125-139
+  StateDB.root                        hook src/blockchain/blockchain.zig:83-85
+  verify_witness                      hook src/engine_api/execution_payload.zig:177-178
+"""
+import numpy as np
+
+from . import gpu
+
+EMPTY_MPT_ROOT = bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421")  # src/mpt/mpt.zig:10
+
+
+def _csr(items, dtype):
+    off = np.zeros(len(items) + 1, dtype)
+    if items:
+        off[1:] = np.cumsum([len(x) for x in items])
+    data = np.frombuffer(b"".join(bytes(x) for x in items) or b"\x00", np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+def keccak256_batch(ctx, msgs):
+    data, off = _csr(msgs, np.uint64)
+    out = np.zeros((len(msgs), 32), np.uint8)
+    ctx.keccak256_batch(data, off, len(msgs), out)
+    return [o.tobytes() for o in out]
+
+
+def keccak256(ctx, data):
+    return keccak256_batch(ctx, [data])[0]
+
+
+def keccak256_with_prefix(ctx, prefix, data):
+    return keccak256(ctx, bytes(prefix) + bytes(data))
+
+
+class KeyVal:
+    """mpt.zig:13-34"""
+
+    def __init__(self, key, value):
+        self.nibbles = [n for b in bytes(key) for n in (b >> 4, b & 15)]
+        self.value = bytes(value)
+
+    init = classmethod(lambda cls, key, value: cls(key, value))
+
+    @staticmethod
+    def less_than(a, b):
+        return a.nibbles < b.nibbles
+
+    def key_bytes(self):
+        return bytes((self.nibbles[i] << 4) | self.nibbles[i + 1] for i in range(0, len(self.nibbles), 2))
+
+
+def mptize(ctx, keyvals):
+    """mpt.zig:38-45; `keyvals` must be sorted by key (the reference asserts) -> PhantGpuError(-1) otherwise"""
+    keys, koff = _csr([kv.key_bytes() for kv in keyvals], np.uint32)
+    vals, voff = _csr([kv.value for kv in keyvals], np.uint64)
+    return ctx.mpt_root(keys, koff, vals, voff, len(keyvals))
+
+
+def _rlp_uint(i):
+    if i == 0:
+        return b"\x80"
+    b = i.to_bytes((i.bit_length() + 7) // 8, "big")
+    return b if len(b) == 1 and b[0] < 0x80 else bytes([0x80 + len(b)]) + b
+
+
+def calculate_mpt_root(ctx, encoded_items):
+    """blockchain.zig:209-235: keys rlp(index) visited in sorted order: 1..0x7f, then 0 (0x80), then 0x80.."""
+    n = len(encoded_items)
+    kv, i = [], 0
+    while i + 1 < n and i + 1 != 0x80:
+        kv.append(KeyVal(bytes([i + 1]), encoded_items[i + 1]))
+        i += 1
+    if n > 0:
+        kv.append(KeyVal(b"\x80", encoded_items[0]))
+        i += 1
+    while i < n:
+        kv.append(KeyVal(_rlp_uint(i), encoded_items[i]))
+        i += 1
+    return mptize(ctx, kv)
+
+
+def payload_list_root(ctx, encoded_items):
+    """execution_payload.zig:125-139: 32-byte big-endian index keys"""
+    return mptize(ctx, [KeyVal(i.to_bytes(32, "big"), v) for i, v in enumerate(encoded_items)])
+
+
+class AccountState:
+    """src/state/types.zig:13-33"""
+
+    def __init__(self, nonce=0, balance=0, code=b"", storage=None):
+        self.nonce, self.balance, self.code, self.storage = nonce, balance, bytes(code), dict(storage or {})
+
+
+class StateDB:
+    """src/state/statedb.zig:16-30 (address -> AccountState) plus the root() the reference lacks"""
+
+    def __init__(self):
+        self.db = {}
+
+    def root(self, ctx):
+        accts = sorted(self.db.items())
+        n = len(accts)
+        one = np.zeros(1, np.uint8)
+        addr = np.frombuffer(b"".join(a for a, _ in accts), np.uint8) if n else one
+        nonce = np.array([s.nonce for _, s in accts], np.uint64) if n else np.zeros(1, np.uint64)
+        bal = np.frombuffer(b"".join(s.balance.to_bytes(32, "big") for _, s in accts), np.uint8) if n else one
+        code, coff = _csr([s.code for _, s in accts], np.uint64)
+        sk, sv, soff = [], [], [0]
+        for _, s in accts:
+            for k, v in s.storage.items():
+                sk.append(int(k).to_bytes(32, "big"))
+                sv.append(int(v).to_bytes(32, "big"))
+            soff.append(len(sk))
+        skeys = np.frombuffer(b"".join(sk), np.uint8) if sk else one
+        svals = np.frombuffer(b"".join(sv), np.uint8) if sv else one
+        return ctx.state_root(n, addr, nonce, bal, code, coff, skeys, svals, np.array(soff, np.uint64))
+
+
+def verify_witness(ctx, state_root, proofs):
+    """proofs: list of (hashed_key32, [node bytes, root first]).  Returns the status list (0 reject / 1 present /
+    2 absent); execution_payload.zig:177-178 would refuse the payload unless none is 0."""
+    n = len(proofs)
+    if n == 0:
+        return []
+    nodes, node_off = _csr([nd for _, chain in proofs for nd in chain], np.uint64)
+    first = np.zeros(n + 1, np.uint64)
+    first[1:] = np.cumsum([len(chain) for _, chain in proofs])
+    keys = np.frombuffer(b"".join(k for k, _ in proofs), np.uint8)
+    root = np.frombuffer(bytes(state_root), np.uint8)
+    status = np.zeros(n, np.uint8)
+    bitmap = np.zeros((n + 63) // 64, np.uint64)
+    ctx.verify_proofs(n, nodes, node_off, first, keys, root, 1, bitmap, status, None, None)
+    return status.tolist()

@@ -1,0 +1,91 @@
+"""The reference's hot-path tests restated against the Python host mirror (phant_b200/host.py)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from phant_b200 import gpu
+    c = gpu.Context(0)
+    yield c
+    c.close()
+
+
+def test_mpt_correctness(ctx):
+    """src/mpt/mpt.zig:316-391 "correctness", line for line."""
+    from phant_b200.host import KeyVal, mptize, EMPTY_MPT_ROOT
+    cases = [
+        ("empty", [], EMPTY_MPT_ROOT.hex()),
+        ("single key - root is a leaf node", [KeyVal.init(bytes([1, 2, 3, 4]), b"hello")],
+         "6764f7ad0efcbc11b84fe7567773aa4b12bd6b4d35c05bbc3951b58dedb6c8e8"),
+        ("two keys - root is a branch node with two (embedded) leaf nodes",
+         [KeyVal.init(bytes([1, 2, 3, 4]), b"hello1"), KeyVal.init(bytes([255, 2, 3, 4]), b"hello2")],
+         "5c474c00e417f587322ae674c948f04e2c217f95bd1dac806af14fa46f8fa403"),
+        ("three keys - two embedded leaves and one hashed node",
+         [KeyVal.init(bytes([1 << 4, 2, 3, 4]), b"hello1"), KeyVal.init(bytes([2 << 4, 2, 3, 4]), b"hello2"),
+          KeyVal.init(bytes([3 << 4, 2, 3, 4]), b"hello333333333333333333333333333")],
+         "86d4d51eedae1cd8ffdfeef48e5f1cd021d84c8d3df0088dfad39e72b37fc4b1"),
+        ("two keys - extension node of 3 nibbles and two leaf nodes",
+         [KeyVal.init(bytes([0, 0xf1, 3, 4]), b"hello1"), KeyVal.init(bytes([0, 0xf2, 3, 4]), b"hello2")],
+         "312b81f16960a816e84679c5b9de49471b07b5c11ef0eff19779b083e418f83b"),
+        ("complex - 5 levels, 3 branch nodes, 2 extension nodes, 4 leaf nodes",
+         [KeyVal.init(bytes([0x34, 0x57, 0x81]), b"hello1"), KeyVal.init(bytes([0x34, 0x57, 0x83]), b"hello2"),
+          KeyVal.init(bytes([0x34, 0x5F, 2, 3]), b"hello3"), KeyVal.init(bytes([0xFF, 1, 2, 3]), b"hello4")],
+         "c66c75a03f2b52dfc32b5e229bb2ff7e1d53dcb2b54fe83a1b39418788e0fc66"),
+        ("complex - one branch node with a value, 40-byte value",
+         [KeyVal.init(bytes([0x34]), b"hello1"), KeyVal.init(bytes([0x34, 0x57, 0x81]), b"hello2"),
+          KeyVal.init(bytes([0x34, 0x57, 0x83]), b"hello3"), KeyVal.init(bytes([0x34, 0x5F, 2, 3]), b"hello4"),
+          KeyVal.init(bytes([0xEF, 1, 2, 3]), b"0123456789012345678901234567890123456789"),
+          KeyVal.init(bytes([0xFF, 1, 2, 3]), b"hello5")],
+         "88a4fc29676ebee58aafcd377acd46af6d29044f9bb8220c50ca8dcfe5153fb3"),
+    ]
+    for name, keyvals, exp in cases:
+        assert mptize(ctx, keyvals).hex() == exp, name
+
+
+def test_block_roots_like_run_block(ctx, golden):
+    """src/blockchain/blockchain.zig:76-90 post-checks: transactions / withdrawals roots of every valid fixture
+    block through calculate_mpt_root, plus the state-root check phant has commented out (:83-85)."""
+    from phant_b200.host import AccountState, StateDB, calculate_mpt_root
+    g = golden("fixture_states.json.gz")
+    tables = {}
+    for key, accounts in g["tables"].items():
+        db = StateDB()
+        for a in accounts:
+            db.db[bytes.fromhex(a["address"])] = AccountState(a["nonce"], int(a["balance"], 16), bytes.fromhex(a["code"]),
+                                                              {int(k, 16): int(v, 16) for k, v in a["storage"].items()})
+        tables[key] = db.root(ctx).hex()
+    for t in g["tests"]:
+        assert tables[t["pre"]] == t["pre_root"]
+        assert tables[t["post"]] == t["post_root"]
+        for b in t["blocks"]:
+            assert calculate_mpt_root(ctx, [bytes.fromhex(x) for x in b["tx_values"]]).hex() == b["transactionsTrie"]
+            assert calculate_mpt_root(ctx, [bytes.fromhex(x) for x in b["wd_values"]]).hex() == b["withdrawalsRoot"]
+
+
+def test_payload_list_root_and_hasher(ctx, oracle):
+    from phant_b200.host import KeyVal, keccak256, keccak256_with_prefix, payload_list_root
+    items = [bytes([i]) * (i + 40) for i in range(130)]
+    want = oracle.mptize([(i.to_bytes(32, "big"), v) for i, v in enumerate(items)])
+    assert payload_list_root(ctx, items) == want
+    assert keccak256(ctx, b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert keccak256_with_prefix(ctx, b"\x02", b"abc") == oracle.keccak256(b"\x02abc")
+    assert KeyVal.less_than(KeyVal(b"\x01", b""), KeyVal(b"\x01\x00", b""))
+
+
+def test_verify_witness(ctx, oracle, golden):
+    from helpers import secure_account_items
+    from phant_b200.host import verify_witness
+    g = golden("fixture_states.json.gz")
+    accounts = max(g["tables"].values(), key=len)[:60]
+    items = secure_account_items(oracle.keccak256, oracle.mptize, accounts)
+    trie = oracle.trie(items)
+    proofs = [(k, trie.prove(k)) for k, _ in items]
+    absent = oracle.keccak256(b"nobody")
+    proofs.append((absent, trie.prove(absent)))
+    st = verify_witness(ctx, trie.root(), proofs)
+    assert st == [1] * len(items) + [2]
+    bad = list(proofs)
+    bad[3] = (bad[3][0], bad[3][1][:-1])
+    assert verify_witness(ctx, trie.root(), bad)[3] == 0
