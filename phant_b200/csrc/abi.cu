@@ -185,7 +185,8 @@ extern "C" int phant_gpu_reset_stats(phant_gpu_ctx* ctx)
 // ------------------------------------------------------------------------------------------------
 // K: hash a CSR message set that is already on the device
 // ------------------------------------------------------------------------------------------------
-int phant_gpu_ctx::hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint64_t total_bytes, uint8_t* d_out)
+int phant_gpu_ctx::hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint64_t total_bytes, uint8_t* d_out,
+                            uint32_t* d_summary)
 {
     phant_gpu_ctx* ctx = this;
     if (n == 0) return PHANT_GPU_OK;
@@ -217,7 +218,7 @@ int phant_gpu_ctx::hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64
         order = (const uint32_t*)d_order.ptr;
     }
     time_begin(0);
-    CU(launch_keccak(stream, device, variant, d_msgs, d_off, order, n, d_out));
+    CU(launch_keccak(stream, device, variant, d_msgs, d_off, order, n, d_out, d_summary));
     time_end();
     stats.launches++;
     stats.keccak_msgs += n;
@@ -287,11 +288,12 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
             }
         }
         if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
-        if (int rc = ctx->hash_csr(in->nodes, in->node_off, n_nodes, total, (uint8_t*)ctx->d_digests.ptr)) return rc;
+        if (int rc = ctx->d_summary.reserve(ctx, 4 * n_nodes + 32)) return rc;
+        if (int rc = ctx->hash_csr(in->nodes, in->node_off, n_nodes, total, (uint8_t*)ctx->d_digests.ptr, (uint32_t*)ctx->d_summary.ptr)) return rc;
         if (accept_bitmap) CU(cudaMemsetAsync(accept_bitmap, 0, bm_bytes, ctx->stream));
         ctx->time_begin(1);
         CU(launch_walk(ctx->stream, ctx->device, np, in->nodes, in->node_off, in->proof_first, in->keys32, in->roots32, in->n_roots,
-                       (const uint8_t*)ctx->d_digests.ptr, accept_bitmap, status, val_off, val_len));
+                       (const uint8_t*)ctx->d_digests.ptr, (const uint32_t*)ctx->d_summary.ptr, accept_bitmap, status, val_off, val_len));
         ctx->time_end();
         ctx->stats.launches++;
         return PHANT_GPU_OK; // asynchronous on the context's stream: phant_gpu_synchronize() to wait
@@ -308,6 +310,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
     if (int rc = ctx->d_keys.reserve(ctx, 32 * np)) return rc;
     if (int rc = ctx->d_roots.reserve(ctx, 32 * in->n_roots)) return rc;
     if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
+    if (int rc = ctx->d_summary.reserve(ctx, 4 * n_nodes + 32)) return rc;
     if (int rc = ctx->d_bitmap.reserve(ctx, bm_bytes)) return rc;
     if (int rc = ctx->d_status.reserve(ctx, np)) return rc;
     if (val_off) if (int rc = ctx->d_voff.reserve(ctx, 8 * np)) return rc;
@@ -362,11 +365,12 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         if (ctx->chunk_events.size() <= chunk) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_events.push_back(e); }
         CU(cudaEventRecord(ctx->chunk_events[chunk], cs));
         CU(cudaStreamWaitEvent(s, ctx->chunk_events[chunk], 0));
-        if (int rc = ctx->hash_csr(d_nodes, d_noff + n0, n1 - n0, b1 - b0, (uint8_t*)ctx->d_digests.ptr + 32 * n0)) return rc;
+        if (int rc = ctx->hash_csr(d_nodes, d_noff + n0, n1 - n0, b1 - b0, (uint8_t*)ctx->d_digests.ptr + 32 * n0,
+                                   (uint32_t*)ctx->d_summary.ptr + n0)) return rc;
         ctx->time_begin(1);
         CU(launch_walk(s, ctx->device, p1 - p0, d_nodes, d_noff, d_pfirst + p0, (const uint8_t*)ctx->d_keys.ptr + 32 * p0,
                        (const uint8_t*)ctx->d_roots.ptr + (in->n_roots == 1 ? 0 : 32 * p0), in->n_roots, (const uint8_t*)ctx->d_digests.ptr,
-                       (uint64_t*)ctx->d_bitmap.ptr + p0 / 64, (uint8_t*)ctx->d_status.ptr + p0, val_off ? (uint64_t*)ctx->d_voff.ptr + p0 : nullptr,
+                       (const uint32_t*)ctx->d_summary.ptr, (uint64_t*)ctx->d_bitmap.ptr + p0 / 64, (uint8_t*)ctx->d_status.ptr + p0, val_off ? (uint64_t*)ctx->d_voff.ptr + p0 : nullptr,
                        val_len ? (uint32_t*)ctx->d_vlen.ptr + p0 : nullptr));
         ctx->time_end();
         ctx->stats.launches++;

@@ -10,14 +10,15 @@ enum KeccakVariant { KECCAK_STAGED = 0, KECCAK_DIRECT = 1, KECCAK_WARP = 2 };
 // keccak_kernels.cu
 int keccak_num_sms(int device);
 cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, const uint8_t* msgs, const uint64_t* off,
-                          const uint32_t* order, uint64_t n, uint8_t* out);
+                          const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary /*nullable*/);
 cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* off, uint64_t n, uint8_t* cls, uint32_t* idx,
                                    unsigned long long* perms);
 
 // walk_kernel.cu
 cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,
                         const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
-                        const uint8_t* digests, uint64_t* bitmap, uint8_t* status, uint64_t* val_off, uint32_t* val_len);
+                        const uint8_t* digests, const uint32_t* summary /*nullable*/, uint64_t* bitmap, uint8_t* status,
+                        uint64_t* val_off, uint32_t* val_len);
 
 // synth.cu
 cudaError_t launch_synth_c2(cudaStream_t s, int device, uint64_t seed, uint64_t first_index, uint64_t n, uint32_t depth,

@@ -31,19 +31,19 @@ struct phant_gpu_ctx {
 
     // staging + scratch (device)
     DevBuf d_msgs, d_off, d_out;                                          // K
-    DevBuf d_first, d_keys, d_roots, d_digests, d_bitmap, d_status, d_voff, d_vlen; // V
+    DevBuf d_first, d_keys, d_roots, d_digests, d_bitmap, d_status, d_voff, d_vlen, d_summary; // V
     DevBuf d_cls, d_cls2, d_idx, d_order, d_cub, d_perms;                 // regrouping
     DevBuf d_tmp_a, d_tmp_b, d_scan_a, d_scan_b;                          // synth / builders
     DevBuf d_b0, d_b1, d_b2, d_b3, d_b4, d_b5, d_b6, d_b7, d_b8, d_b9;    // trie builder scratch
     DevBuf st_in, st_hash, st_seg, st_tmp, st_sort, st_acc;               // state-root staging
     bool perms_init = false, perms_pending = false;
 
-    std::array<DevBuf*, 37> all_bufs()
+    std::array<DevBuf*, 38> all_bufs()
     {
         return {&d_msgs, &d_off, &d_out, &d_first, &d_keys, &d_roots, &d_digests, &d_bitmap, &d_status, &d_voff, &d_vlen,
                 &d_cls, &d_cls2, &d_idx, &d_order, &d_cub, &d_perms, &d_tmp_a, &d_tmp_b, &d_scan_a, &d_scan_b,
                 &d_b0, &d_b1, &d_b2, &d_b3, &d_b4, &d_b5, &d_b6, &d_b7, &d_b8, &d_b9,
-                &st_in, &st_hash, &st_seg, &st_tmp, &st_sort, &st_acc};
+                &st_in, &st_hash, &st_seg, &st_tmp, &st_sort, &st_acc, &d_summary};
     }
 
     // device timing of the dominant kernels: event pairs recorded on `stream`, resolved lazily
@@ -57,7 +57,8 @@ struct phant_gpu_ctx {
     void resolve_times();
 
     int fail(cudaError_t e, const char* what, const char* file, int line);
-    int hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint64_t total_bytes, uint8_t* d_out);
+    int hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint64_t total_bytes, uint8_t* d_out,
+                 uint32_t* d_summary = nullptr);
     // trie.cu
     int build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off, uint32_t n,
                      const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots);

@@ -24,18 +24,56 @@
 namespace phant {
 
 // ------------------------------------------------------------------------------------------------
+// node summary for the proof walk (walk_kernel.cu): while a node's bytes sit in shared memory / L1 for hashing,
+// classify it once.  A SIMPLE BRANCH is a strictly canonical 17-item list (rule R2 of DESIGN.md) whose 16 children
+// are each empty (0x80) or a 32-byte hash (0xa0 ..) and whose value is empty -- by far the common trie node.
+// For those the walk needs no parse: summary = mask of hash children, header size, kind 1; the child for nibble n
+// sits at hdr + 33*popc(mask & ((1<<n)-1)) + (n - popc(..)).  Everything else gets summary 0 = "walk parses it".
+// The summary does not depend on the key, so it is also right for witness nodes shared between proofs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t summarize_node(const uint8_t* p, uint32_t len)
+{
+    if (len < 18) return 0;
+    const uint32_t b0 = p[0];
+    uint32_t hdr, pay;
+    if (b0 < 0xc0) return 0;
+    if (b0 <= 0xf7) { hdr = 1; pay = b0 - 0xc0; }
+    else {
+        const uint32_t n = b0 - 0xf7;
+        if (n > 2 || p[1] == 0) return 0;
+        pay = n == 1 ? p[1] : ((uint32_t)p[1] << 8) | p[2];
+        if (pay <= 55) return 0;
+        hdr = 1 + n;
+    }
+    if (hdr + pay != len) return 0;
+    uint32_t o = hdr, mask = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < 16; ++i) {
+        if (o >= len) return 0;
+        const uint32_t c = p[o];
+        if (c == 0x80) o += 1;
+        else if (c == 0xa0) { mask |= 1u << i; o += 33; }
+        else return 0;
+    }
+    if (o + 1 != len || p[o] != 0x80) return 0;
+    return (mask << 8) | (hdr << 2) | 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
 // direct
 // ------------------------------------------------------------------------------------------------
 template <int UNROLL>
 __global__ void __launch_bounds__(128)
 keccak256_direct_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
-                        const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out)
+                        const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out,
+                        uint32_t* __restrict__ summary)
 {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t m = order ? order[i] : i;
         const uint64_t beg = off[m], end = off[m + 1];
         uint64_t dg[4];
         keccak256_thread<UNROLL>(msgs + beg, end - beg, dg);
+        if (summary) summary[m] = (end - beg) <= 4096 ? summarize_node(msgs + beg, (uint32_t)(end - beg)) : 0;
         uint64_t* o = reinterpret_cast<uint64_t*>(out + 32 * m);
         o[0] = dg[0]; o[1] = dg[1]; o[2] = dg[2]; o[3] = dg[3];
     }
@@ -85,7 +123,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int UNROLL>
 __global__ void __launch_bounds__(STAGE_WARPS * 32)
 keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
-                        const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out)
+                        const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out,
+                        uint32_t* __restrict__ summary)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,6 +150,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
 #pragma unroll
         for (int i = 0; i < 25; ++i) st[i] = 0;
         bool done = !active;
+        bool first_trip = true;
 
         while (!__all_sync(0xffffffffu, done)) {
             // -- ask the copy engine for this lane's next <= 4 blocks (16-byte aligned window) --
@@ -133,6 +173,8 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
                 const uint64_t in_slot = cs - skew; // message bytes present in the slot (cs == 0 -> need == 0)
                 const uint64_t avail = need < in_slot ? need : in_slot;
                 const MsgView v = msg_view(slot + skew);
+                if (summary && first_trip) // the whole node is in the slot iff the message ends in this window
+                    summary[m] = avail == need ? summarize_node(slot + skew, (uint32_t)need) : 0;
                 const uint32_t nfull = (uint32_t)(avail / KECCAK_RATE);
                 uint32_t base = 0;
                 for (uint32_t b = 0; b < nfull; ++b) {
@@ -146,6 +188,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
                     cur += (uint64_t)nfull * KECCAK_RATE;
                 }
             }
+            first_trip = false;
         }
         if (active) {
             uint4* o = reinterpret_cast<uint4*>(out + 32 * m);
@@ -265,7 +308,7 @@ int keccak_num_sms(int device)
 }
 
 cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, const uint8_t* msgs, const uint64_t* off,
-                          const uint32_t* order, uint64_t n, uint8_t* out)
+                          const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary)
 {
     if (n == 0) return cudaSuccess;
     const int sms = keccak_num_sms(device);
@@ -282,14 +325,14 @@ cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, con
         uint64_t blocks = (tiles + STAGE_WARPS - 1) / STAGE_WARPS;
         const uint64_t cap = (uint64_t)sms * 3; // 3 CTAs of 71.8 KB fit one SM
         if (blocks > cap) blocks = cap;
-        keccak256_staged_kernel<2><<<(unsigned)blocks, STAGE_WARPS * 32, STAGE_SMEM, s>>>(msgs, off, order, n, out);
+        keccak256_staged_kernel<2><<<(unsigned)blocks, STAGE_WARPS * 32, STAGE_SMEM, s>>>(msgs, off, order, n, out, summary);
         break;
     }
     case KECCAK_DIRECT: {
         uint64_t blocks = (n + 127) / 128;
         const uint64_t cap = (uint64_t)sms * 8;
         if (blocks > cap) blocks = cap;
-        keccak256_direct_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(msgs, off, order, n, out);
+        keccak256_direct_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(msgs, off, order, n, out, summary);
         break;
     }
     case KECCAK_WARP: {
@@ -297,6 +340,7 @@ cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, con
         const uint64_t cap = (uint64_t)sms * 8;
         if (blocks > cap) blocks = cap;
         keccak256_warp_kernel<<<(unsigned)blocks, 256, 0, s>>>(msgs, off, n, out);
+        if (summary) cudaMemsetAsync(summary, 0, 4 * n, s); // this layout does not classify: the walk parses every node
         break;
     }
     }

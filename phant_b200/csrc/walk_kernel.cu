@@ -94,7 +94,7 @@ __constant__ uint8_t EMPTY_ROOT[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55,
 
 __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off, uint64_t first,
                         uint64_t last, const uint8_t* __restrict__ key, const uint8_t* __restrict__ root,
-                        const uint8_t* __restrict__ digests, uint64_t& voff, uint32_t& vlen)
+                        const uint8_t* __restrict__ digests, const uint32_t* __restrict__ summary, uint64_t& voff, uint32_t& vlen)
 {
     voff = 0; vlen = 0;
     uint32_t expect[8];
@@ -116,7 +116,19 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
             cur = nodes + o;
             cur_len = (uint32_t)l;
             if (!eq32_aligned(digests + 32 * i, expect)) return ST_REJECT; // R1
+            // fast path: the hash kernel already proved this node a simple branch (canonical 17-item list, children
+            // empty or 32-byte hashes, empty value) and left the child mask: no parse, one 32-byte fetch
+            const uint32_t sm = summary ? summary[i] : 0;
             ++i;
+            if ((sm & 3u) == 1u && pos < 64) {
+                const uint32_t nibble = (pos & 1) ? (key[pos >> 1] & 15u) : (key[pos >> 1] >> 4);
+                ++pos;
+                const uint32_t mask = sm >> 8;
+                if (!((mask >> nibble) & 1u)) return i == last ? ST_ABSENT : ST_REJECT; // empty slot (R3)
+                const uint32_t before = __popc(mask & ((1u << nibble) - 1u));
+                load32(cur + ((sm >> 2) & 7u) + 33u * before + (nibble - before) + 1u, expect);
+                continue;
+            }
         }
         Item top;
         const uint32_t tot = rlp_item(cur, cur_len, top);
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(128)
 walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
             const uint64_t* __restrict__ proof_first, const uint8_t* __restrict__ keys32,
             const uint8_t* __restrict__ roots32, uint64_t n_roots, const uint8_t* __restrict__ digests,
-            uint64_t* __restrict__ bitmap, uint8_t* __restrict__ status, uint64_t* __restrict__ val_off,
+            const uint32_t* __restrict__ summary, uint64_t* __restrict__ bitmap, uint8_t* __restrict__ status, uint64_t* __restrict__ val_off,
             uint32_t* __restrict__ val_len)
 {
     const uint64_t n_padded = (n_proofs + 31) & ~(uint64_t)31; // whole warps, so the ballot is complete
@@ -220,7 +232,7 @@ walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t
             uint64_t vo;
             uint32_t vl;
             st = walk_one(nodes, node_off, proof_first[p], proof_first[p + 1], keys32 + 32 * p,
-                          roots32 + (n_roots == 1 ? 0 : 32 * p), digests, vo, vl);
+                          roots32 + (n_roots == 1 ? 0 : 32 * p), digests, summary, vo, vl);
             if (status) status[p] = (uint8_t)st;
             if (val_off) val_off[p] = vo;
             if (val_len) val_len[p] = vl;
@@ -234,13 +246,14 @@ walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t
 
 cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,
                         const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
-                        const uint8_t* digests, uint64_t* bitmap, uint8_t* status, uint64_t* val_off, uint32_t* val_len)
+                        const uint8_t* digests, const uint32_t* summary, uint64_t* bitmap, uint8_t* status, uint64_t* val_off,
+                        uint32_t* val_len)
 {
     if (n_proofs == 0) return cudaSuccess;
     uint64_t blocks = (n_proofs + 127) / 128;
     const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
     if (blocks > cap) blocks = cap;
-    walk_kernel<<<(unsigned)blocks, 128, 0, s>>>(n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, digests,
+    walk_kernel<<<(unsigned)blocks, 128, 0, s>>>(n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, digests, summary,
                                                  bitmap, status, val_off, val_len);
     return cudaGetLastError();
 }
