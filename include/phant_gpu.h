@@ -127,6 +127,10 @@ typedef struct {
     uint64_t n_roots;
     uint64_t n_nodes;            /* = proof_first[n_proofs]; may be 0 = "read it from the arrays" (host pointers: */
     uint64_t nodes_bytes;        /* = node_off[n_nodes];      always derived; device pointers: costs a sync)      */
+    /* Deduplicated witness (optional): when node_index is not NULL, `nodes` holds every DISTINCT node once
+     * (n_nodes of them -- required), each is hashed once, and proof p walks the nodes
+     * node_index[proof_first[p] .. proof_first[p+1]).  NULL = chains are contiguous runs of `nodes`. */
+    const uint64_t* node_index;
 } phant_gpu_proof_batch;
 int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap,
                             uint8_t* status, uint64_t* val_off, uint32_t* val_len);

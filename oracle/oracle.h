@@ -79,6 +79,7 @@ typedef struct {
     const uint8_t* keys32;       /* n_proofs*32 */
     const uint8_t* roots32;      /* n_roots*32 */
     uint64_t n_roots;            /* 1 (broadcast) or n_proofs */
+    const uint64_t* node_index;  /* NULL, or deduplicated witness: proof p walks nodes node_index[proof_first[p] ..] */
 } oracle_proof_batch;
 /* status[n_proofs] (may be NULL), bitmap = ceil(n/64) words (may be NULL),
  * val_off/val_len[n_proofs] (may be NULL): byte slice of `nodes` holding the proven value. */
@@ -106,6 +107,12 @@ void oracle_synth_c2(uint64_t seed, uint64_t first_index, uint64_t n, uint32_t d
 void oracle_synth_c3_sizes(uint64_t seed, uint64_t first_index, uint64_t n, uint32_t* n_nodes, uint32_t* n_bytes);
 void oracle_synth_c3(uint64_t seed, uint64_t first_index, uint64_t n, int corrupt, uint8_t* nodes,
                      uint64_t* node_off, uint64_t* proof_first, uint8_t* keys32, uint8_t* roots32, int threads);
+
+/* C5: deduplicated block witnesses (oracle/blocks.c).  Outputs are malloc'd; release with oracle_free. */
+int oracle_synth_blocks(uint64_t seed, uint64_t first_block, uint32_t n_blocks, uint32_t txs_per_block, int threads, uint8_t** nodes,
+                        uint64_t** node_off, uint64_t** node_index, uint64_t** proof_first, uint8_t** keys32, uint8_t** roots32,
+                        uint32_t** block_of_proof, uint64_t totals[4]);
+void oracle_free(void* p);
 
 #ifdef __cplusplus
 }

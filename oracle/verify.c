@@ -27,7 +27,7 @@ static const uint8_t EMPTY_ROOT[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55,
                                        0xe6, 0x92, 0xc0, 0xf8, 0x6e, 0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c,
                                        0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
 
-static int verify_one(const uint8_t* nodes, const uint64_t* node_off, uint64_t first, uint64_t last,
+static int verify_one(const uint8_t* nodes, const uint64_t* node_off, const uint64_t* node_index, uint64_t first, uint64_t last,
                       const uint8_t* key32, const uint8_t* root32, uint64_t* voff, uint32_t* vlen)
 {
     *voff = 0;
@@ -49,8 +49,9 @@ static int verify_one(const uint8_t* nodes, const uint64_t* node_off, uint64_t f
     for (;;) {
         if (!embedded) {
             if (i == last) return ST_REJECT; /* hash reference without a node to resolve it */
-            cur = nodes + node_off[i];
-            cur_len = node_off[i + 1] - node_off[i];
+            const uint64_t ni = node_index ? node_index[i] : i; /* deduplicated witness: chains hold node indices */
+            cur = nodes + node_off[ni];
+            cur_len = node_off[ni + 1] - node_off[ni];
             uint8_t h[32];
             oracle_keccak256(cur, cur_len, h);
             if (memcmp(h, expect, 32) != 0) return ST_REJECT;
@@ -149,7 +150,7 @@ void oracle_verify_proofs(const oracle_proof_batch* in, uint64_t* accept_bitmap,
             const uint8_t* root = in->roots32 + (in->n_roots == 1 ? 0 : 32 * p);
             uint64_t vo;
             uint32_t vl;
-            int st = verify_one(in->nodes, in->node_off, in->proof_first[p], in->proof_first[p + 1],
+            int st = verify_one(in->nodes, in->node_off, in->node_index, in->proof_first[p], in->proof_first[p + 1],
                                 in->keys32 + 32 * p, root, &vo, &vl);
             if (status) status[p] = (uint8_t)st;
             if (val_off) val_off[p] = vo;

@@ -266,6 +266,60 @@ extern "C" int phant_gpu_keccak256_batch(phant_gpu_ctx* ctx, const uint8_t* msgs
 // ------------------------------------------------------------------------------------------------
 // V: proof verification
 // ------------------------------------------------------------------------------------------------
+// host pointers + deduplicated witness: distinct nodes are hashed once, chains are index lists (one shot, no chunking:
+// a chunk of proofs does not map to a contiguous range of nodes)
+static int verify_dedup_host(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap, uint8_t* status,
+                             uint64_t* val_off, uint32_t* val_len)
+{
+    const uint64_t np = in->n_proofs, n_nodes = in->n_nodes;
+    if (n_nodes == 0) return PHANT_GPU_E_INVALID;
+    uint64_t total = 0;
+    if (int rc = check_offsets_host(in->node_off, n_nodes, &total)) return rc;
+    if (total && !in->nodes) return PHANT_GPU_E_INVALID;
+    for (uint64_t p = 0; p < np; ++p)
+        if (in->proof_first[p + 1] < in->proof_first[p]) return PHANT_GPU_E_INVALID;
+    const uint64_t n_refs = in->proof_first[np];
+    for (uint64_t r = 0; r < n_refs; ++r)
+        if (in->node_index[r] >= n_nodes) return PHANT_GPU_E_INVALID;
+    const size_t bm_bytes = ((np + 63) / 64) * 8;
+    if (int rc = ctx->d_msgs.reserve(ctx, total + 64)) return rc;
+    if (int rc = ctx->d_off.reserve(ctx, 8 * (n_nodes + 1))) return rc;
+    if (int rc = ctx->d_first.reserve(ctx, 8 * (np + 1))) return rc;
+    if (int rc = ctx->d_index.reserve(ctx, 8 * (n_refs + 1))) return rc;
+    if (int rc = ctx->d_keys.reserve(ctx, 32 * np)) return rc;
+    if (int rc = ctx->d_roots.reserve(ctx, 32 * in->n_roots)) return rc;
+    if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
+    if (int rc = ctx->d_summary.reserve(ctx, 4 * n_nodes + 32)) return rc;
+    if (int rc = ctx->d_bitmap.reserve(ctx, bm_bytes)) return rc;
+    if (int rc = ctx->d_status.reserve(ctx, np)) return rc;
+    if (val_off) if (int rc = ctx->d_voff.reserve(ctx, 8 * np)) return rc;
+    if (val_len) if (int rc = ctx->d_vlen.reserve(ctx, 4 * np)) return rc;
+    cudaStream_t s = ctx->stream;
+    if (total) CU(cudaMemcpyAsync(ctx->d_msgs.ptr, in->nodes, total, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_off.ptr, in->node_off, 8 * (n_nodes + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_first.ptr, in->proof_first, 8 * (np + 1), cudaMemcpyHostToDevice, s));
+    if (n_refs) CU(cudaMemcpyAsync(ctx->d_index.ptr, in->node_index, 8 * n_refs, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_keys.ptr, in->keys32, 32 * np, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_roots.ptr, in->roots32, 32 * in->n_roots, cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += total + 8 * (n_nodes + 1) + 8 * (np + 1) + 8 * n_refs + 32 * np + 32 * in->n_roots;
+    if (int rc = ctx->hash_csr((const uint8_t*)ctx->d_msgs.ptr, (const uint64_t*)ctx->d_off.ptr, n_nodes, total, (uint8_t*)ctx->d_digests.ptr,
+                               (uint32_t*)ctx->d_summary.ptr)) return rc;
+    CU(cudaMemsetAsync(ctx->d_bitmap.ptr, 0, bm_bytes, s));
+    ctx->time_begin(1);
+    CU(launch_walk(s, ctx->device, np, (const uint8_t*)ctx->d_msgs.ptr, (const uint64_t*)ctx->d_off.ptr, (const uint64_t*)ctx->d_index.ptr,
+                   (const uint64_t*)ctx->d_first.ptr, (const uint8_t*)ctx->d_keys.ptr, (const uint8_t*)ctx->d_roots.ptr, in->n_roots,
+                   (const uint8_t*)ctx->d_digests.ptr, (const uint32_t*)ctx->d_summary.ptr, (uint64_t*)ctx->d_bitmap.ptr,
+                   (uint8_t*)ctx->d_status.ptr, val_off ? (uint64_t*)ctx->d_voff.ptr : nullptr, val_len ? (uint32_t*)ctx->d_vlen.ptr : nullptr));
+    ctx->time_end();
+    ctx->stats.launches++;
+    if (accept_bitmap) { CU(cudaMemcpyAsync(accept_bitmap, ctx->d_bitmap.ptr, bm_bytes, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += bm_bytes; }
+    if (status) { CU(cudaMemcpyAsync(status, ctx->d_status.ptr, np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += np; }
+    if (val_off) { CU(cudaMemcpyAsync(val_off, ctx->d_voff.ptr, 8 * np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += 8 * np; }
+    if (val_len) { CU(cudaMemcpyAsync(val_len, ctx->d_vlen.ptr, 4 * np, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += 4 * np; }
+    CU(cudaStreamSynchronize(s));
+    return PHANT_GPU_OK;
+}
+
 extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap,
                                        uint8_t* status, uint64_t* val_off, uint32_t* val_len)
 {
@@ -279,6 +333,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
 
     if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) {
         uint64_t n_nodes = in->n_nodes, total = in->nodes_bytes;
+        if (in->node_index && n_nodes == 0) return PHANT_GPU_E_INVALID; // the number of distinct nodes cannot be derived
         if (n_nodes == 0) { // not supplied: read the tails of the CSR arrays back (one sync each)
             CU(cudaMemcpyAsync(&n_nodes, in->proof_first + np, 8, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
@@ -292,7 +347,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         if (int rc = ctx->hash_csr(in->nodes, in->node_off, n_nodes, total, (uint8_t*)ctx->d_digests.ptr, (uint32_t*)ctx->d_summary.ptr)) return rc;
         if (accept_bitmap) CU(cudaMemsetAsync(accept_bitmap, 0, bm_bytes, ctx->stream));
         ctx->time_begin(1);
-        CU(launch_walk(ctx->stream, ctx->device, np, in->nodes, in->node_off, in->proof_first, in->keys32, in->roots32, in->n_roots,
+        CU(launch_walk(ctx->stream, ctx->device, np, in->nodes, in->node_off, in->node_index, in->proof_first, in->keys32, in->roots32, in->n_roots,
                        (const uint8_t*)ctx->d_digests.ptr, (const uint32_t*)ctx->d_summary.ptr, accept_bitmap, status, val_off, val_len));
         ctx->time_end();
         ctx->stats.launches++;
@@ -300,6 +355,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
     }
 
     // host pointers: validate the CSR arrays, stage everything, run, copy the verdicts back
+    if (in->node_index) return verify_dedup_host(ctx, in, accept_bitmap, status, val_off, val_len);
     // (the CSR arrays are validated chunk by chunk below, while the previous chunk's DMA is in flight)
     const uint64_t n_nodes = in->proof_first[np];
     const uint64_t total = in->node_off[n_nodes];
@@ -368,7 +424,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         if (int rc = ctx->hash_csr(d_nodes, d_noff + n0, n1 - n0, b1 - b0, (uint8_t*)ctx->d_digests.ptr + 32 * n0,
                                    (uint32_t*)ctx->d_summary.ptr + n0)) return rc;
         ctx->time_begin(1);
-        CU(launch_walk(s, ctx->device, p1 - p0, d_nodes, d_noff, d_pfirst + p0, (const uint8_t*)ctx->d_keys.ptr + 32 * p0,
+        CU(launch_walk(s, ctx->device, p1 - p0, d_nodes, d_noff, nullptr, d_pfirst + p0, (const uint8_t*)ctx->d_keys.ptr + 32 * p0,
                        (const uint8_t*)ctx->d_roots.ptr + (in->n_roots == 1 ? 0 : 32 * p0), in->n_roots, (const uint8_t*)ctx->d_digests.ptr,
                        (const uint32_t*)ctx->d_summary.ptr, (uint64_t*)ctx->d_bitmap.ptr + p0 / 64, (uint8_t*)ctx->d_status.ptr + p0, val_off ? (uint64_t*)ctx->d_voff.ptr + p0 : nullptr,
                        val_len ? (uint32_t*)ctx->d_vlen.ptr + p0 : nullptr));

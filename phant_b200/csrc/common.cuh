@@ -16,7 +16,7 @@ cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* o
 
 // walk_kernel.cu
 cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,
-                        const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
+                        const uint64_t* node_index /*nullable*/, const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
                         const uint8_t* digests, const uint32_t* summary /*nullable*/, uint64_t* bitmap, uint8_t* status,
                         uint64_t* val_off, uint32_t* val_len);
 

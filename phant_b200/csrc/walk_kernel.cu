@@ -92,7 +92,8 @@ __constant__ uint8_t EMPTY_ROOT[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55,
                                        0xe6, 0x92, 0xc0, 0xf8, 0x6e, 0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c,
                                        0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
 
-__device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off, uint64_t first,
+__device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
+                        const uint64_t* __restrict__ node_index, uint64_t first,
                         uint64_t last, const uint8_t* __restrict__ key, const uint8_t* __restrict__ root,
                         const uint8_t* __restrict__ digests, const uint32_t* __restrict__ summary, uint64_t& voff, uint32_t& vlen)
 {
@@ -110,15 +111,16 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
     for (;;) {
         if (!embedded) {
             if (i == last) return ST_REJECT; // R3: a hash reference needs a node
-            const uint64_t o = node_off[i];
-            const uint64_t l = node_off[i + 1] - o;
+            const uint64_t ni = node_index ? node_index[i] : i; // deduplicated witness: the chain holds node indices
+            const uint64_t o = node_off[ni];
+            const uint64_t l = node_off[ni + 1] - o;
             if (l > 0xffffffffull) return ST_REJECT;
             cur = nodes + o;
             cur_len = (uint32_t)l;
-            if (!eq32_aligned(digests + 32 * i, expect)) return ST_REJECT; // R1
+            if (!eq32_aligned(digests + 32 * ni, expect)) return ST_REJECT; // R1
             // fast path: the hash kernel already proved this node a simple branch (canonical 17-item list, children
             // empty or 32-byte hashes, empty value) and left the child mask: no parse, one 32-byte fetch
-            const uint32_t sm = summary ? summary[i] : 0;
+            const uint32_t sm = summary ? summary[ni] : 0;
             ++i;
             if ((sm & 3u) == 1u && pos < 64) {
                 const uint32_t nibble = (pos & 1) ? (key[pos >> 1] & 15u) : (key[pos >> 1] >> 4);
@@ -220,7 +222,7 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
 
 __global__ void __launch_bounds__(128)
 walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
-            const uint64_t* __restrict__ proof_first, const uint8_t* __restrict__ keys32,
+            const uint64_t* __restrict__ node_index, const uint64_t* __restrict__ proof_first, const uint8_t* __restrict__ keys32,
             const uint8_t* __restrict__ roots32, uint64_t n_roots, const uint8_t* __restrict__ digests,
             const uint32_t* __restrict__ summary, uint64_t* __restrict__ bitmap, uint8_t* __restrict__ status, uint64_t* __restrict__ val_off,
             uint32_t* __restrict__ val_len)
@@ -231,7 +233,7 @@ walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t
         if (p < n_proofs) {
             uint64_t vo;
             uint32_t vl;
-            st = walk_one(nodes, node_off, proof_first[p], proof_first[p + 1], keys32 + 32 * p,
+            st = walk_one(nodes, node_off, node_index, proof_first[p], proof_first[p + 1], keys32 + 32 * p,
                           roots32 + (n_roots == 1 ? 0 : 32 * p), digests, summary, vo, vl);
             if (status) status[p] = (uint8_t)st;
             if (val_off) val_off[p] = vo;
@@ -245,7 +247,7 @@ walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t
 } // namespace
 
 cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,
-                        const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
+                        const uint64_t* node_index, const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
                         const uint8_t* digests, const uint32_t* summary, uint64_t* bitmap, uint8_t* status, uint64_t* val_off,
                         uint32_t* val_len)
 {
@@ -253,7 +255,7 @@ cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uin
     uint64_t blocks = (n_proofs + 127) / 128;
     const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
     if (blocks > cap) blocks = cap;
-    walk_kernel<<<(unsigned)blocks, 128, 0, s>>>(n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, digests, summary,
+    walk_kernel<<<(unsigned)blocks, 128, 0, s>>>(n_proofs, nodes, node_off, node_index, proof_first, keys32, roots32, n_roots, digests, summary,
                                                  bitmap, status, val_off, val_len);
     return cudaGetLastError();
 }

@@ -40,7 +40,7 @@ class Accounts(C.Structure):
 class ProofBatch(C.Structure):
     _fields_ = [("n_proofs", C.c_uint64), ("nodes", C.c_void_p), ("node_off", C.c_void_p), ("proof_first", C.c_void_p),
                 ("keys32", C.c_void_p), ("roots32", C.c_void_p), ("n_roots", C.c_uint64), ("n_nodes", C.c_uint64),
-                ("nodes_bytes", C.c_uint64)]
+                ("nodes_bytes", C.c_uint64), ("node_index", C.c_void_p)]
 
 
 class TrieDesc(C.Structure):
@@ -172,9 +172,9 @@ class Context:
 
     # V
     def verify_proofs(self, n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, bitmap=None, status=None,
-                      val_off=None, val_len=None, n_nodes=0, nodes_bytes=0):
+                      val_off=None, val_len=None, n_nodes=0, nodes_bytes=0, node_index=None):
         b = ProofBatch(n_proofs, _ptr(nodes), _ptr(node_off), _ptr(proof_first), _ptr(keys32), _ptr(roots32), n_roots,
-                       n_nodes, nodes_bytes)
+                       n_nodes, nodes_bytes, _ptr(node_index))
         self._chk(_lib().phant_gpu_verify_proofs(self._h, C.byref(b), _ptr(bitmap), _ptr(status), _ptr(val_off), _ptr(val_len)),
                   "verify_proofs")
 

@@ -50,7 +50,7 @@ class Accounts(C.Structure):
 
 class ProofBatch(C.Structure):
     _fields_ = [("n_proofs", C.c_uint64), ("nodes", u8p), ("node_off", u64p), ("proof_first", u64p), ("keys32", u8p),
-                ("roots32", u8p), ("n_roots", C.c_uint64)]
+                ("roots32", u8p), ("n_roots", C.c_uint64), ("node_index", u64p)]
 
 
 KECCAK_FN = C.CFUNCTYPE(None, u8p, C.c_size_t, u8p)
@@ -170,11 +170,12 @@ class Oracle:
         return out.tobytes()
 
     # -- proofs --
-    def verify_proofs(self, nodes, node_off, proof_first, keys32, roots32, threads=1):
+    def verify_proofs(self, nodes, node_off, proof_first, keys32, roots32, threads=1, node_index=None):
         n = len(proof_first) - 1
         n_roots = roots32.size // 32
         nodes = np.ascontiguousarray(nodes)
-        b = ProofBatch(n, _p(nodes, u8p), _p(node_off, u64p), _p(proof_first, u64p), _p(keys32, u8p), _p(roots32, u8p), n_roots)
+        b = ProofBatch(n, _p(nodes, u8p), _p(node_off, u64p), _p(proof_first, u64p), _p(keys32, u8p), _p(roots32, u8p), n_roots,
+                       _p(node_index, u64p))
         bitmap = np.zeros((n + 63) // 64, np.uint64)
         status = np.zeros(max(n, 1), np.uint8)
         voff = np.zeros(max(n, 1), np.uint64)
@@ -206,6 +207,25 @@ class Oracle:
         self.lib.oracle_synth_c3(seed, first, n, int(corrupt), _p(nodes, u8p), _p(node_off, u64p), _p(first_arr, u64p),
                                  _p(keys, u8p), _p(roots, u8p), threads)
         return nodes, node_off, first_arr, keys, roots
+
+    def synth_blocks(self, n_blocks, txs=300, first=0, seed=0x5048414E54, threads=8):
+        """C5: deduplicated block witnesses -> dict of numpy arrays (copies; the C buffers are freed)"""
+        L = self.lib
+        L.oracle_synth_blocks.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int] + [C.POINTER(C.c_void_p)] * 7 + [u64p]
+        L.oracle_free.argtypes = [C.c_void_p]
+        ptrs = [C.c_void_p() for _ in range(7)]
+        totals = (C.c_uint64 * 4)()
+        L.oracle_synth_blocks(seed, first, n_blocks, txs, threads, *[C.byref(p) for p in ptrs], totals)
+        tn, tb, ti, tp = (int(x) for x in totals)
+
+        def take(p, dtype, count):
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(count,)).copy()
+            L.oracle_free(p)
+            return a
+        return dict(nodes=np.concatenate([take(ptrs[0], np.uint8, tb + 64)]), node_off=take(ptrs[1], np.uint64, tn + 1),
+                    node_index=take(ptrs[2], np.uint64, ti + 1)[:ti], proof_first=take(ptrs[3], np.uint64, tp + 1),
+                    keys32=take(ptrs[4], np.uint8, 32 * tp + 32)[:32 * tp], roots32=take(ptrs[5], np.uint8, 32 * tp + 32)[:32 * tp],
+                    block_of_proof=take(ptrs[6], np.uint32, tp + 1)[:tp], n_nodes=tn, n_bytes=tb, n_refs=ti, n_proofs=tp)
 
     # -- complete trie --
     def ctrie(self, depth, seed=0x5048414E54):

@@ -166,3 +166,69 @@ def test_host_pipeline_many_chunks_and_bad_csr(ctx, oracle):
     # and the context is still usable afterwards
     got = gpu_verify(ctx, *o)
     assert (got[1] == want[1]).all()
+
+
+def test_deduplicated_block_witness(ctx, oracle):
+    """config C5 shape: per-block virtual tries, distinct nodes stored once, chains are node-index lists; verdicts,
+    bitmap and value slices must equal the oracle's, host-pointer and device-pointer paths alike."""
+    import torch
+    from phant_b200 import gpu
+    w = oracle.synth_blocks(60, txs=50, first=0, threads=8)      # blocks 37 is corrupted
+    n = w["n_proofs"]
+    want = oracle.verify_proofs(w["nodes"], w["node_off"], w["proof_first"], w["keys32"], w["roots32"], threads=8, node_index=w["node_index"])
+    assert w["n_refs"] > w["n_nodes"]                              # something is shared
+    bitmap = np.zeros((n + 63) // 64, np.uint64)
+    status = np.full(n, 77, np.uint8)
+    voff = np.zeros(n, np.uint64)
+    vlen = np.zeros(n, np.uint32)
+    ctx.set_flags(0)
+    ctx.verify_proofs(n, w["nodes"], w["node_off"], w["proof_first"], w["keys32"], w["roots32"], n, bitmap, status, voff, vlen,
+                      n_nodes=w["n_nodes"], nodes_bytes=w["n_bytes"], node_index=w["node_index"])
+    assert (status == want[1]).all() and (bitmap == want[0]).all()
+    ok = want[1] == 1
+    assert (voff[ok] == want[2][ok]).all() and (vlen[ok] == want[3][ok]).all()
+    rej_blocks = set(w["block_of_proof"][status == 0].tolist())
+    assert rej_blocks == {37}
+    # device pointers
+    d = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v).cuda() for k, v in w.items() if isinstance(v, np.ndarray)}
+    d_status = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+    ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+    ctx.verify_proofs(n, d["nodes"], d["node_off"], d["proof_first"], d["keys32"], d["roots32"], n, d_bitmap, d_status, None, None,
+                      n_nodes=w["n_nodes"], nodes_bytes=w["n_bytes"], node_index=d["node_index"])
+    ctx.synchronize()
+    ctx.set_flags(0)
+    assert (d_status.cpu().numpy() == want[1]).all()
+    # a node index out of range is refused, not dereferenced
+    bad = w["node_index"].copy()
+    bad[5] = w["n_nodes"] + 3
+    with pytest.raises(gpu.PhantGpuError) as e:
+        ctx.verify_proofs(n, w["nodes"], w["node_off"], w["proof_first"], w["keys32"], w["roots32"], n, bitmap, status, None, None,
+                          n_nodes=w["n_nodes"], nodes_bytes=w["n_bytes"], node_index=bad)
+    assert e.value.code == -1
+
+
+def test_full_size_c3_property(ctx):
+    """BASELINE config: 10M storage proofs, mixed depth 4..12 (28 GB of nodes in HBM); reject iff index % 97 == 0."""
+    import torch
+    from phant_b200 import gpu
+    n = 10_000_000
+    n_nodes, n_bytes = ctx.synth_sizes(3, n)
+    d_nodes = torch.empty(n_bytes + 64, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(n_nodes + 1, dtype=torch.int64, device="cuda")
+    d_first = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    d_keys = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    d_roots = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    ctx.synth(3, n, d_nodes, d_off, d_first, d_keys, d_roots)
+    d_status = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+    ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+    ctx.verify_proofs(n, d_nodes, d_off, d_first, d_keys, d_roots, n, d_bitmap, d_status, None, None, n_nodes=n_nodes, nodes_bytes=n_bytes)
+    ctx.synchronize()
+    ctx.set_flags(0)
+    depth = (d_first[1:] - d_first[:-1]).cpu().numpy()
+    assert depth.min() == 4 and depth.max() == 12
+    expect = np.where(np.arange(n) % 97 == 0, 0, 1)
+    assert (d_status.cpu().numpy() == expect).all()
+    del d_nodes, d_off
+    torch.cuda.empty_cache()
