@@ -162,6 +162,24 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(gpu_index):
+    """Restrict this process to the CPUs NVML reports as local to the GPU (same socket as its PCIe root), so the
+    pinned host buffers of the e2e leg are allocated on that socket's memory.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)[0], len(cpus)
+    except Exception:  # noqa: BLE001 -- no NVML / no permission: keep the default placement
+        pass
+    return None
+
+
 def run_gpu(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -170,6 +188,7 @@ def run_gpu(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(local_rank)  # pinned staging buffers are then first-touched next to this GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = gpu.Context(local_rank)
@@ -315,7 +334,7 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e["h2d_bytes"] // e2e_steps,
                     "d2h_bytes_per_step": st_e["d2h_bytes"] // e2e_steps, "steps": e2e_steps,
                     "ms_per_step": 1e3 * float(t_e.item()) / e2e_steps},
-            "gpu_launches": int(st["launches"]), "clocks": clocks,
+            "gpu_launches": int(st["launches"]), "clocks": clocks, "host_numa_pin": numa,
             "parity": {"status_ok": status_ok, "bitmap_ok": bitmap_ok, "e2e_ok": e2e_ok},
         }
         if world == 1 and not args.no_cpu:
