@@ -134,6 +134,56 @@ __device__ __forceinline__ void absorb_final(uint64_t (&st)[25], const MsgView& 
     keccak_f1600<UNROLL>(st);
 }
 
+// ---- shared-memory absorb (staged kernel) -------------------------------------------------------
+// The message sits in the lane's shared-memory slot at byte address `sa` (any alignment).  Read it as aligned
+// 32-bit words (LDS.32 on the LSU pipe) and fix the byte skew with ONE funnel shift per word: 34 SHF + 34 LOP3 on
+// the ALU pipe per 136-byte block, against ~180 for the generic 64-bit path above.
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+template <int UNROLL>
+__device__ __forceinline__ void absorb_full_smem(uint64_t (&st)[25], uint32_t sa)
+{
+    const uint32_t a4 = sa & ~3u, sh = (sa & 3u) * 8;
+    uint32_t w[2 * KECCAK_RATE_WORDS + 1];
+#pragma unroll
+    for (int j = 0; j < 2 * KECCAK_RATE_WORDS; ++j) w[j] = lds32(a4 + 4 * j);
+    w[2 * KECCAK_RATE_WORDS] = sh ? lds32(a4 + 4 * 2 * KECCAK_RATE_WORDS) : 0; // holds block bytes only when skewed
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_WORDS; ++k) {
+        const uint32_t lo = __funnelshift_r(w[2 * k], w[2 * k + 1], sh);
+        const uint32_t hi = __funnelshift_r(w[2 * k + 1], w[2 * k + 2], sh);
+        st[k] ^= ((uint64_t)hi << 32) | lo;
+    }
+    keccak_f1600<UNROLL>(st);
+}
+// last block: rem < 136 message bytes at `sa`, then the 0x01 .. 0x80 padding.  Reads at most 4 bytes past the
+// message (inside the slot or its 16-byte tail pad); whatever is read beyond `rem` is masked off.
+template <int UNROLL>
+__device__ __forceinline__ void absorb_final_smem(uint64_t (&st)[25], uint32_t sa, uint32_t rem)
+{
+    const uint32_t a4 = sa & ~3u, sh = (sa & 3u) * 8;
+    uint32_t prev = rem ? lds32(a4) : 0;
+#pragma unroll
+    for (int j = 0; j < 2 * KECCAK_RATE_WORDS; ++j) {
+        const int valid = (int)rem - 4 * j; // message bytes in 32-bit word j
+        uint32_t word = 0, next = 0;
+        if (valid > 0) {
+            next = lds32(a4 + 4 * (j + 1));
+            word = __funnelshift_r(prev, next, sh);
+            if (valid < 4) word &= (1u << (8 * valid)) - 1u;
+        }
+        if (valid >= 0 && valid < 4) word ^= 1u << (8 * valid);
+        if (j == 2 * KECCAK_RATE_WORDS - 1) word ^= 0x80000000u;
+        st[j >> 1] ^= (j & 1) ? ((uint64_t)word << 32) : (uint64_t)word;
+        prev = next;
+    }
+    keccak_f1600<UNROLL>(st);
+}
+
 // Whole-message Keccak-256 from global or shared memory (generic pointer), any alignment.
 template <int UNROLL = 2>
 __device__ __forceinline__ void keccak256_thread(const uint8_t* p, uint64_t len, uint64_t (&digest)[4])

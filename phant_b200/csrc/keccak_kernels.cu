@@ -21,6 +21,9 @@
 #include "common.cuh"
 #include "keccak_f1600.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace phant {
 
 // ------------------------------------------------------------------------------------------------
@@ -82,11 +85,15 @@ keccak256_direct_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
 // ------------------------------------------------------------------------------------------------
 // staged: bulk-copy engine -> per-lane shared-memory slot -> registers
 // ------------------------------------------------------------------------------------------------
-constexpr int STAGE_BLOCKS = 4;                                    // rate blocks per trip
-constexpr int STAGE_SLOT = 560;                                    // 4*136 + 15 rounded to 16; 16*35 (odd)
-constexpr int STAGE_WARPS = 4;
-constexpr int STAGE_SMEM = 128 + STAGE_WARPS * 32 * STAGE_SLOT;    // barriers + slots = 71,808 B -> 3 CTAs/SM
-static_assert(STAGE_SLOT % 16 == 0 && STAGE_SLOT >= STAGE_BLOCKS * KECCAK_RATE + 15, "slot too small");
+// slot = BLOCKS rate blocks + 15 bytes of skew, rounded to 16 x odd so that the 16-byte windows of a quarter warp fall
+// in distinct banks; + 16 bytes behind the last slot because the final-block reader may touch 4 bytes past a message
+constexpr int stage_slot(int blocks)
+{
+    int s = (blocks * KECCAK_RATE + 15 + 15) / 16;
+    if (s % 2 == 0) ++s;
+    return 16 * s;
+}
+constexpr int stage_smem(int blocks, int warps) { return 128 + warps * 32 * stage_slot(blocks) + 16; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -120,8 +127,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(STAGE_WARPS * 32)
+template <int UNROLL, int BLOCKS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
                         const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out,
                         uint32_t* __restrict__ summary)
@@ -129,7 +136,8 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar = smem_u32(smem) + 8 * warp;
-    uint8_t* slot = smem + 128 + (warp * 32 + lane) * STAGE_SLOT;
+    constexpr int SLOT = stage_slot(BLOCKS);
+    uint8_t* slot = smem + 128 + (warp * 32 + lane) * SLOT;
     const uint32_t slot_s = smem_u32(slot);
     if (lane == 0) mbar_init(bar, 32);
     fence_proxy_async();
@@ -137,7 +145,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
     uint32_t parity = 0;
 
     const uint64_t n_tiles = (n + 31) / 32;
-    for (uint64_t tile = (uint64_t)blockIdx.x * STAGE_WARPS + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * STAGE_WARPS) {
+    for (uint64_t tile = (uint64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * WARPS) {
         const uint64_t idx = tile * 32 + lane;
         const bool active = idx < n;
         uint64_t m = 0, cur = 0, end = 0;
@@ -159,7 +167,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
             uint32_t cs = 0;
             if (need) {
                 const uint64_t span = ((end - a0) + 15) & ~(uint64_t)15;
-                cs = span < STAGE_SLOT ? (uint32_t)span : STAGE_SLOT;
+                cs = span < SLOT ? (uint32_t)span : SLOT;
                 fence_proxy_async(); // my earlier reads of the slot are ordered before the engine's writes
                 mbar_arrive_expect_tx(bar, cs);
                 bulk_g2s(slot_s, msgs + a0, cs, bar);
@@ -172,17 +180,16 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
                 const uint32_t skew = (uint32_t)(cur - a0);
                 const uint64_t in_slot = cs - skew; // message bytes present in the slot (cs == 0 -> need == 0)
                 const uint64_t avail = need < in_slot ? need : in_slot;
-                const MsgView v = msg_view(slot + skew);
                 if (summary && first_trip) // the whole node is in the slot iff the message ends in this window
                     summary[m] = avail == need ? summarize_node(slot + skew, (uint32_t)need) : 0;
                 const uint32_t nfull = (uint32_t)(avail / KECCAK_RATE);
-                uint32_t base = 0;
+                uint32_t sa = slot_s + skew;
                 for (uint32_t b = 0; b < nfull; ++b) {
-                    absorb_full<UNROLL>(st, v, base);
-                    base += KECCAK_RATE_WORDS;
+                    absorb_full_smem<UNROLL>(st, sa);
+                    sa += KECCAK_RATE;
                 }
                 if (avail == need) { // the message ends inside this window: pad and finish
-                    absorb_final<UNROLL>(st, v, base, (uint32_t)(avail - (uint64_t)nfull * KECCAK_RATE));
+                    absorb_final_smem<UNROLL>(st, sa, (uint32_t)(avail - (uint64_t)nfull * KECCAK_RATE));
                     done = true;
                 } else {
                     cur += (uint64_t)nfull * KECCAK_RATE;
@@ -307,6 +314,27 @@ int keccak_num_sms(int device)
     return cached[device] ? cached[device] : 148;
 }
 
+template <int BLOCKS, int WARPS>
+static cudaError_t launch_staged(cudaStream_t s, int sms, const uint8_t* msgs, const uint64_t* off, const uint32_t* order, uint64_t n,
+                                 uint8_t* out, uint32_t* summary)
+{
+    constexpr int SMEM = stage_smem(BLOCKS, WARPS);
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        cudaError_t e = cudaFuncSetAttribute(keccak256_staged_kernel<2, BLOCKS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(keccak256_staged_kernel<2, BLOCKS, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, keccak256_staged_kernel<2, BLOCKS, WARPS>, WARPS * 32, SMEM);
+        if (e != cudaSuccess || ctas_per_sm < 1) { ctas_per_sm = 0; return e != cudaSuccess ? e : cudaErrorLaunchOutOfResources; }
+    }
+    const uint64_t tiles = (n + 31) / 32;
+    uint64_t blocks = (tiles + WARPS - 1) / WARPS;
+    const uint64_t cap = (uint64_t)sms * ctas_per_sm; // persistent: every CTA resident, striding over the tiles
+    if (blocks > cap) blocks = cap;
+    keccak256_staged_kernel<2, BLOCKS, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, s>>>(msgs, off, order, n, out, summary);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, const uint8_t* msgs, const uint64_t* off,
                           const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary)
 {
@@ -314,19 +342,29 @@ cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, con
     const int sms = keccak_num_sms(device);
     switch (variant) {
     case KECCAK_STAGED: {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(keccak256_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_SMEM);
-            if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(keccak256_staged_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            attr_set = true;
+        // tuning knob (development): PHANT_STAGE_CFG=b<blocks>w<warps>; the default is the measured best
+        static int cfg = -1;
+        if (cfg < 0) {
+            const char* e = getenv("PHANT_STAGE_CFG");
+            cfg = 0;
+            if (e) {
+                const char* names[] = {"default", "b3w4", "b2w4", "b1w4", "b4w8", "b2w8", "b4w12", "b4w6", "b3w8", "b4w10", "b4w4"};
+                for (int i = 0; i < 11; ++i) if (!strcmp(e, names[i])) cfg = i;
+            }
         }
-        const uint64_t tiles = (n + 31) / 32;
-        uint64_t blocks = (tiles + STAGE_WARPS - 1) / STAGE_WARPS;
-        const uint64_t cap = (uint64_t)sms * 3; // 3 CTAs of 71.8 KB fit one SM
-        if (blocks > cap) blocks = cap;
-        keccak256_staged_kernel<2><<<(unsigned)blocks, STAGE_WARPS * 32, STAGE_SMEM, s>>>(msgs, off, order, n, out, summary);
-        break;
+        switch (cfg) {
+        case 1: return launch_staged<3, 4>(s, sms, msgs, off, order, n, out, summary);
+        case 2: return launch_staged<2, 4>(s, sms, msgs, off, order, n, out, summary);
+        case 3: return launch_staged<1, 4>(s, sms, msgs, off, order, n, out, summary);
+        case 4: return launch_staged<4, 8>(s, sms, msgs, off, order, n, out, summary);
+        case 5: return launch_staged<2, 8>(s, sms, msgs, off, order, n, out, summary);
+        case 6: return launch_staged<4, 12>(s, sms, msgs, off, order, n, out, summary);
+        case 7: return launch_staged<4, 6>(s, sms, msgs, off, order, n, out, summary);
+        case 8: return launch_staged<3, 8>(s, sms, msgs, off, order, n, out, summary);
+        case 9: return launch_staged<4, 10>(s, sms, msgs, off, order, n, out, summary);
+        case 10: return launch_staged<4, 4>(s, sms, msgs, off, order, n, out, summary);
+        default: return launch_staged<4, 12>(s, sms, msgs, off, order, n, out, summary); // measured best: 1 CTA of 12 warps per SM
+        }
     }
     case KECCAK_DIRECT: {
         uint64_t blocks = (n + 127) / 128;
