@@ -6,9 +6,10 @@
 //   staged  (default)  one sponge per thread, state in registers; each lane's message bytes are brought
 //                      from HBM into its private shared-memory slot by the bulk-copy engine
 //                      (cp.async.bulk -> SASS UBLKCP, completion on a per-warp mbarrier), 4 rate blocks
-//                      per trip, and read back as 64-bit words.  No thread ever issues a global load
-//                      for message bytes, so the strided (one-message-per-lane) access pattern never
-//                      reaches the LSU as 32 uncoalesced sectors.
+//                      per trip, and read back as aligned 32-bit words (one funnel shift fixes the byte
+//                      skew).  No thread ever issues a global load for message bytes, so the strided
+//                      (one-message-per-lane) access pattern never reaches the LSU as 32 uncoalesced
+//                      sectors.  One CTA of 12 warps per SM (215 KB of slots).
 //   direct             same sponge, message words loaded straight from global memory (fallback when
 //                      the buffer is not 16-byte aligned / padded; also the simplest correct kernel).
 //   warp               the layout BASELINE.json's north star describes: one WARP per sponge, lane i
@@ -315,11 +316,12 @@ int keccak_num_sms(int device)
 }
 
 template <int BLOCKS, int WARPS>
-static cudaError_t launch_staged(cudaStream_t s, int sms, const uint8_t* msgs, const uint64_t* off, const uint32_t* order, uint64_t n,
+static cudaError_t launch_staged(cudaStream_t s, int device, int sms, const uint8_t* msgs, const uint64_t* off, const uint32_t* order, uint64_t n,
                                  uint8_t* out, uint32_t* summary)
 {
     constexpr int SMEM = stage_smem(BLOCKS, WARPS);
-    static int ctas_per_sm = 0;
+    static int ctas_cache[64] = {0}; // function attributes are per device
+    int& ctas_per_sm = ctas_cache[(device >= 0 && device < 64) ? device : 0];
     if (!ctas_per_sm) {
         cudaError_t e = cudaFuncSetAttribute(keccak256_staged_kernel<2, BLOCKS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
@@ -353,17 +355,17 @@ cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, con
             }
         }
         switch (cfg) {
-        case 1: return launch_staged<3, 4>(s, sms, msgs, off, order, n, out, summary);
-        case 2: return launch_staged<2, 4>(s, sms, msgs, off, order, n, out, summary);
-        case 3: return launch_staged<1, 4>(s, sms, msgs, off, order, n, out, summary);
-        case 4: return launch_staged<4, 8>(s, sms, msgs, off, order, n, out, summary);
-        case 5: return launch_staged<2, 8>(s, sms, msgs, off, order, n, out, summary);
-        case 6: return launch_staged<4, 12>(s, sms, msgs, off, order, n, out, summary);
-        case 7: return launch_staged<4, 6>(s, sms, msgs, off, order, n, out, summary);
-        case 8: return launch_staged<3, 8>(s, sms, msgs, off, order, n, out, summary);
-        case 9: return launch_staged<4, 10>(s, sms, msgs, off, order, n, out, summary);
-        case 10: return launch_staged<4, 4>(s, sms, msgs, off, order, n, out, summary);
-        default: return launch_staged<4, 12>(s, sms, msgs, off, order, n, out, summary); // measured best: 1 CTA of 12 warps per SM
+        case 1: return launch_staged<3, 4>(s, device, sms, msgs, off, order, n, out, summary);
+        case 2: return launch_staged<2, 4>(s, device, sms, msgs, off, order, n, out, summary);
+        case 3: return launch_staged<1, 4>(s, device, sms, msgs, off, order, n, out, summary);
+        case 4: return launch_staged<4, 8>(s, device, sms, msgs, off, order, n, out, summary);
+        case 5: return launch_staged<2, 8>(s, device, sms, msgs, off, order, n, out, summary);
+        case 6: return launch_staged<4, 12>(s, device, sms, msgs, off, order, n, out, summary);
+        case 7: return launch_staged<4, 6>(s, device, sms, msgs, off, order, n, out, summary);
+        case 8: return launch_staged<3, 8>(s, device, sms, msgs, off, order, n, out, summary);
+        case 9: return launch_staged<4, 10>(s, device, sms, msgs, off, order, n, out, summary);
+        case 10: return launch_staged<4, 4>(s, device, sms, msgs, off, order, n, out, summary);
+        default: return launch_staged<4, 12>(s, device, sms, msgs, off, order, n, out, summary); // measured best: 1 CTA of 12 warps per SM
         }
     }
     case KECCAK_DIRECT: {

@@ -1,0 +1,85 @@
+#!/usr/bin/env python3
+"""Timings of the builder entry points M / S / U on one GPU next to the CPU oracle (development tool).
+One JSON object per line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib  # noqa: E402
+from phant_b200 import gpu  # noqa: E402
+
+
+def timeit(fn, reps):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def main():
+    o = oracle_lib.get()
+    o.use_reference_keccak(True)
+    ctx = gpu.Context(0)
+    rng = np.random.default_rng(1)
+    # ---- M: index trie of 400 withdrawals (fixture scale) and secure tries of growing size ----
+    from helpers import index_trie_items
+    wd = [rng.integers(0, 256, 48, dtype=np.uint8).tobytes() for _ in range(400)]
+    kv = index_trie_items(wd)
+    keys, koff = oracle_lib.csr([k for k, _ in kv], np.uint32)
+    vals, voff = oracle_lib.csr([v for _, v in kv], np.uint64)
+    g = timeit(lambda: ctx.mpt_root(keys, koff, vals, voff, len(kv)), 20)
+    c = timeit(lambda: o.mptize(kv), 20)
+    print(json.dumps({"what": "M 400-item index trie", "gpu_ms": g * 1e3, "cpu_ms": c * 1e3}), flush=True)
+    for n in (10_000, 200_000, 2_000_000):
+        k = np.unique(rng.integers(0, 256, (n, 32), dtype=np.uint8), axis=0)
+        n = len(k)
+        keys = np.ascontiguousarray(k.reshape(-1))
+        koff = (np.arange(n + 1) * 32).astype(np.uint32)
+        vals = rng.integers(0, 256, n * 80, dtype=np.uint8)
+        voff = (np.arange(n + 1) * 80).astype(np.uint64)
+        ctx.reset_stats()
+        g = timeit(lambda: ctx.mpt_root(keys, koff, vals, voff, n), 3)
+        st = ctx.stats()
+        t0 = time.perf_counter()
+        out = np.zeros(32, np.uint8)
+        rc = o.lib.oracle_mptize(keys.ctypes.data_as(oracle_lib.u8p), koff.ctypes.data_as(oracle_lib.u32p), vals.ctypes.data_as(oracle_lib.u8p),
+                                 voff.ctypes.data_as(oracle_lib.u64p), n, out.ctypes.data_as(oracle_lib.u8p))
+        c = time.perf_counter() - t0
+        assert rc == 0 and ctx.mpt_root(keys, koff, vals, voff, n) == out.tobytes()
+        print(json.dumps({"what": f"M secure trie {n} keys x 80 B", "gpu_ms": g * 1e3, "cpu_1thread_ms": c * 1e3, "launches_per_call": st["launches"] // 4,
+                          "keys_per_s_gpu": n / g}), flush=True)
+    # ---- U: config C4 ----
+    t = ctx.trie_open(6)
+    n = 100_000
+    pos = rng.choice(16 ** 6, size=n, replace=False).astype(np.uint32)
+    keys = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    keys[:, 0] = (pos >> 16) & 0xff
+    keys[:, 1] = (pos >> 8) & 0xff
+    keys[:, 2] = pos & 0xff
+    flat = np.ascontiguousarray(keys.reshape(-1))
+    v = rng.integers(0, 256, n * 78, dtype=np.uint8)
+    voff = (np.arange(n + 1) * 78).astype(np.uint32)
+    ctx.reset_stats()
+    g = timeit(lambda: t.update(flat, v, voff, n), 10)
+    st = ctx.stats()
+    oc = o.ctrie(6)
+    vals_list = [v[78 * i:78 * i + 78].tobytes() for i in range(n)]
+    t0 = time.perf_counter()
+    r = oc.update(flat, vals_list)
+    c = time.perf_counter() - t0
+    assert r == t.update(flat, v, voff, n)
+    print(json.dumps({"what": "U C4: 100k dirty leaves into 16^6-leaf trie (host pointers)", "gpu_ms": g * 1e3, "cpu_1thread_ms": c * 1e3,
+                      "launches_per_call": st["launches"] // 11, "keccak_ms_per_call": st["keccak_ms"] / 11}), flush=True)
+    t.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
