@@ -135,6 +135,14 @@ typedef struct {
 int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap,
                             uint8_t* status, uint64_t* val_off, uint32_t* val_len);
 
+/* B -- logs blooms (row N3 of SURVEY.md 8f): Receipt.calculateLogsBloom / addToBloom
+ * (src/types/receipt.zig:37-63) for many receipts at once.  items = the bloom inputs (log addresses 20 B, topics
+ * 32 B, ...) CSR; bloom_of_item[i] says which of the n_blooms 2048-bit filters item i belongs to.  Each item is
+ * hashed (same batched Keccak kernel) and sets 3 bits: for j in 0..2, bit 0x7ff - (be16(hash[2j..2j+2]) & 0x7ff),
+ * most significant bit of byte 0 first.  blooms = n_blooms * 256 bytes (zeroed by the call). */
+int phant_gpu_logs_bloom(phant_gpu_ctx* ctx, const uint8_t* items, const uint64_t* item_off, const uint32_t* bloom_of_item,
+                         uint64_t n_items, uint64_t n_blooms, uint8_t* blooms);
+
 /* U -- resident trie + dirty-frontier root recompute (BASELINE.json "state-root recompute").
  * Round-1 shape: a complete 16-ary trie with `depth` branch levels (16^depth leaves) whose untouched
  * leaf hashes come from the synthetic PRNG; update rewrites n_dirty leaves (distinct leaf positions)

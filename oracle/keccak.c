@@ -106,3 +106,20 @@ void oracle_keccak256_batch(const uint8_t* msgs, const uint64_t* off, uint64_t n
 #pragma omp parallel for num_threads(threads) schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) fn(msgs + off[i], (size_t)(off[i + 1] - off[i]), out32 + 32 * i);
 }
+
+/* logs bloom: Receipt.addToBloom (src/types/receipt.zig:50-63; same arithmetic as evmone/test/state/bloom_filter.cpp:17-31) */
+void oracle_logs_bloom(const uint8_t* items, const uint64_t* item_off, const uint32_t* bloom_of_item, uint64_t n_items,
+                       uint64_t n_blooms, uint8_t* blooms)
+{
+    memset(blooms, 0, 256 * n_blooms);
+    for (uint64_t i = 0; i < n_items; ++i) {
+        uint8_t h[32];
+        oracle_keccak256(items + item_off[i], item_off[i + 1] - item_off[i], h);
+        uint8_t* bloom = blooms + 256 * (uint64_t)bloom_of_item[i];
+        for (int j = 0; j < 3; ++j) {
+            unsigned bit_to_set = (((unsigned)h[2 * j] << 8) | h[2 * j + 1]) & 0x07ff;
+            unsigned bit_index = 0x07ff - bit_to_set;
+            bloom[bit_index / 8] |= (uint8_t)(1u << (7 - bit_index % 8));
+        }
+    }
+}

@@ -35,6 +35,10 @@ int oracle_use_ref_keccak(const char* so_path);
 /* CSR batch: msg i = msgs[off[i] .. off[i+1]).  threads<=1 -> serial. */
 void oracle_keccak256_batch(const uint8_t* msgs, const uint64_t* off, uint64_t n, uint8_t* out32, int threads);
 
+/* logs bloom (src/types/receipt.zig:37-63): item i sets 3 bits in bloom bloom_of_item[i]; blooms = n_blooms*256 bytes */
+void oracle_logs_bloom(const uint8_t* items, const uint64_t* item_off, const uint32_t* bloom_of_item, uint64_t n_items,
+                       uint64_t n_blooms, uint8_t* blooms);
+
 /* ---- mptize (follows src/mpt/mpt.zig:38-314) ----
  * keys: byte strings sorted lexicographically (a strict prefix sorts first), CSR; values CSR.
  * Returns 0, or -1 if keys are not strictly sorted (the reference asserts sortedness, mpt.zig:39). */

@@ -441,6 +441,79 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
 }
 
 // ------------------------------------------------------------------------------------------------
+// B: logs blooms (src/types/receipt.zig:37-63)
+// ------------------------------------------------------------------------------------------------
+__global__ void bloom_set_kernel(const uint8_t* __restrict__ digests, const uint32_t* __restrict__ bloom_of_item, uint64_t n_items,
+                                 uint64_t n_blooms, uint32_t* __restrict__ blooms /* n_blooms * 64 words */)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = bloom_of_item[i];
+        if (b >= n_blooms) continue; // validated on the host for host pointers; never write out of bounds
+        const uint8_t* h = digests + 32 * i;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const uint32_t bit_to_set = (((uint32_t)h[2 * j] << 8) | h[2 * j + 1]) & 0x07ffu; // big-endian 16-bit word, low 11 bits
+            const uint32_t bit_index = 0x07ffu - bit_to_set;
+            const uint32_t byte_index = bit_index >> 3;
+            const uint32_t in_byte = 1u << (7 - (bit_index & 7));
+            atomicOr(&blooms[64 * b + (byte_index >> 2)], in_byte << (8 * (byte_index & 3)));
+        }
+    }
+}
+
+extern "C" int phant_gpu_logs_bloom(phant_gpu_ctx* ctx, const uint8_t* items, const uint64_t* item_off, const uint32_t* bloom_of_item,
+                                    uint64_t n_items, uint64_t n_blooms, uint8_t* blooms)
+{
+    if (!ctx || (n_blooms && !blooms) || (n_items && (!item_off || !bloom_of_item))) return PHANT_GPU_E_INVALID;
+    if (n_blooms == 0) return n_items ? PHANT_GPU_E_INVALID : PHANT_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool dev = ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS;
+    const uint8_t* d_items = items; const uint64_t* d_ioff = item_off; const uint32_t* d_map = bloom_of_item;
+    uint32_t* d_blooms = (uint32_t*)blooms;
+    uint64_t total = 0;
+    if (!dev) {
+        if (n_items) {
+            if (int rc = check_offsets_host(item_off, n_items, &total)) return rc;
+            if (total && !items) return PHANT_GPU_E_INVALID;
+            for (uint64_t i = 0; i < n_items; ++i) if (bloom_of_item[i] >= n_blooms) return PHANT_GPU_E_INVALID;
+        }
+        if (int rc = ctx->d_msgs.reserve(ctx, total + 64)) return rc;
+        if (int rc = ctx->d_off.reserve(ctx, 8 * (n_items + 1))) return rc;
+        if (int rc = ctx->d_index.reserve(ctx, 4 * (n_items + 1))) return rc;
+        if (int rc = ctx->d_out.reserve(ctx, 256 * n_blooms)) return rc;
+        if (total) CU(cudaMemcpyAsync(ctx->d_msgs.ptr, items, total, cudaMemcpyHostToDevice, s));
+        if (n_items) {
+            CU(cudaMemcpyAsync(ctx->d_off.ptr, item_off, 8 * (n_items + 1), cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(ctx->d_index.ptr, bloom_of_item, 4 * n_items, cudaMemcpyHostToDevice, s));
+        }
+        ctx->stats.h2d_bytes += total + 12 * n_items + 8;
+        d_items = (const uint8_t*)ctx->d_msgs.ptr; d_ioff = (const uint64_t*)ctx->d_off.ptr; d_map = (const uint32_t*)ctx->d_index.ptr;
+        d_blooms = (uint32_t*)ctx->d_out.ptr;
+    } else if (n_items) {
+        CU(cudaMemcpyAsync(&total, item_off + n_items, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    CU(cudaMemsetAsync(d_blooms, 0, 256 * n_blooms, s));
+    if (n_items) {
+        if (int rc = ctx->d_digests.reserve(ctx, 32 * n_items + 32)) return rc;
+        if (int rc = ctx->hash_csr(d_items, d_ioff, n_items, total, (uint8_t*)ctx->d_digests.ptr)) return rc;
+        uint64_t blocks = (n_items + 255) / 256;
+        const uint64_t cap = (uint64_t)keccak_num_sms(ctx->device) * 8;
+        if (blocks > cap) blocks = cap;
+        bloom_set_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint8_t*)ctx->d_digests.ptr, d_map, n_items, n_blooms, d_blooms);
+        CU(cudaGetLastError());
+        ctx->stats.launches++;
+    }
+    if (!dev) {
+        CU(cudaMemcpyAsync(blooms, d_blooms, 256 * n_blooms, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += 256 * n_blooms;
+        CU(cudaStreamSynchronize(s));
+    }
+    return PHANT_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // synthetic witnesses (device pointers)
 // ------------------------------------------------------------------------------------------------
 namespace phant { uint64_t synth_c2_bytes_per_proof(uint32_t depth); }

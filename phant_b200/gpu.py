@@ -51,7 +51,7 @@ EXPORTS = [
     "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_set_stream", "phant_gpu_strerror",
     "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
     "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_state_root", "phant_gpu_verify_proofs",
-    "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
+    "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
 ]
 
@@ -84,6 +84,7 @@ def _lib():
     L.phant_gpu_mpt_root.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_state_root.argtypes = [vp, C.POINTER(Accounts), vp]
     L.phant_gpu_verify_proofs.argtypes = [vp, C.POINTER(ProofBatch), vp, vp, vp, vp]
+    L.phant_gpu_logs_bloom.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64, vp]
     L.phant_gpu_trie_open.argtypes = [vp, C.POINTER(TrieDesc), C.POINTER(vp)]
     L.phant_gpu_trie_root.argtypes = [vp, vp]
     L.phant_gpu_trie_update.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
@@ -177,6 +178,11 @@ class Context:
                        n_nodes, nodes_bytes, _ptr(node_index))
         self._chk(_lib().phant_gpu_verify_proofs(self._h, C.byref(b), _ptr(bitmap), _ptr(status), _ptr(val_off), _ptr(val_len)),
                   "verify_proofs")
+
+    # B
+    def logs_bloom(self, items, item_off, bloom_of_item, n_items, n_blooms, blooms):
+        self._chk(_lib().phant_gpu_logs_bloom(self._h, _ptr(items), _ptr(item_off), _ptr(bloom_of_item), n_items, n_blooms, _ptr(blooms)),
+                  "logs_bloom")
 
     # U
     def trie_open(self, depth, seed=0x5048414E54, kind=0):

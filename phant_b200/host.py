@@ -122,6 +122,33 @@ class StateDB:
         return ctx.state_root(n, addr, nonce, bal, code, coff, skeys, svals, np.array(soff, np.uint64))
 
 
+class Log:
+    """src/types/receipt.zig:65-69"""
+
+    def __init__(self, address, topics, data=b""):
+        self.address, self.topics, self.data = bytes(address), [bytes(t) for t in topics], bytes(data)
+
+
+def calculate_logs_blooms(ctx, receipts_logs):
+    """Receipt.calculateLogsBloom (src/types/receipt.zig:37-48) for a whole block: receipts_logs = one list of Log per
+    receipt -> (list of 256-byte blooms, block bloom = their OR, the check disabled at src/blockchain/blockchain.zig:86-88)"""
+    items, owner = [], []
+    for r, logs in enumerate(receipts_logs):
+        for log in logs:
+            items.append(log.address)
+            owner.append(r)
+            for t in log.topics:
+                items.append(t)
+                owner.append(r)
+    n = len(receipts_logs)
+    blooms = np.zeros((max(n, 1), 256), np.uint8)
+    if n:
+        data, off = _csr(items, np.uint64)
+        ctx.logs_bloom(data, off, np.array(owner or [0], np.uint32), len(items), n, blooms)
+    block = np.bitwise_or.reduce(blooms[:n], axis=0) if n else np.zeros(256, np.uint8)
+    return [b.tobytes() for b in blooms[:n]], block.tobytes()
+
+
 def verify_witness(ctx, state_root, proofs):
     """proofs: list of (hashed_key32, [node bytes, root first]).  Returns the status list (0 reject / 1 present /
     2 absent); execution_payload.zig:177-178 would refuse the payload unless none is 0."""

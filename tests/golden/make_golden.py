@@ -122,6 +122,23 @@ def evmone_kat():
     ]
     for s in states:
         assert s["root"] in hsrc or s["name"] == "empty", s["name"]
+    # logs bloom of the three-log receipt quoted in state_mpt_hash_test.cpp:118-190 (Sepolia tx 0x1e68d9db...)
+    addr = "84bf5c35c54a994c72ff9d8b4cca8f5034153a2c"
+    logs = [[addr, ["0109fc6f55cf40689f02fbaad7af7fe7bbac8a3d2186600afc7d3e10cac60271",
+                    "00000000000000000000000000000000000000000000000000000000000027b6",
+                    "00000000000000000000000038dc84830b92d171d7b4c129c813360d6ab8b54e"]],
+            [addr, ["92e98423f8adac6e64d0608e519fd1cefb861498385c6dee70d58fc926ddc68c",
+                    "00000000000000000000000000000000000000000000000000000000481f2280",
+                    "00000000000000000000000000000000000000000000000000000000000027b6",
+                    "00000000000000000000000038dc84830b92d171d7b4c129c813360d6ab8b54e"]],
+            [addr, ["fe25c73e3b9089fac37d55c4c7efcba6f04af04cebd2fc4d6d7dbb07e1e5234f",
+                    "000000000000000000000000000000000000000000000c958b4bca4282ac0000"]]]
+    bloom = re.search(r'"logsBloom":\s*//\s*"0x([0-9a-f]{512})"', hsrc).group(1)  # first receipt in the file: the three-log one
+    assert bloom.startswith("0000001100000000")
+    for _, topics in logs:
+        for t in topics:
+            assert t in hsrc
+    dump("logs_bloom_kat.json", {"source": "evmone/test/unittests/state_mpt_hash_test.cpp:118-190", "logs": logs, "bloom": bloom})
     dump("evmone_mpt_kat.json", {"source": "evmone/test/unittests/state_mpt_test.cpp:20-333, state_mpt_hash_test.cpp:19-66",
                                  "topologies": groups, "examples": examples, "states": states})
 

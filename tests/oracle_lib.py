@@ -130,6 +130,14 @@ class Oracle:
         self.lib.oracle_keccak256_batch(_p(msgs, u8p), _p(off, u64p), n, _p(out, u8p), threads)
         return out
 
+    def logs_bloom(self, items, owner, n_blooms):
+        data, off = csr(items)
+        own = np.array(owner or [0], np.uint32)
+        out = np.zeros((max(n_blooms, 1), 256), np.uint8)
+        self.lib.oracle_logs_bloom.argtypes = [u8p, u64p, u32p, C.c_uint64, C.c_uint64, u8p]
+        self.lib.oracle_logs_bloom(_p(data, u8p), _p(off, u64p), _p(own, u32p), len(items), n_blooms, _p(out, u8p))
+        return out[:n_blooms]
+
     # -- mptize --
     def mptize(self, kv):
         keys, koff = csr([k for k, _ in kv], np.uint32)

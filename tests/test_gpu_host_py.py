@@ -89,3 +89,30 @@ def test_verify_witness(ctx, oracle, golden):
     bad = list(proofs)
     bad[3] = (bad[3][0], bad[3][1][:-1])
     assert verify_witness(ctx, trie.root(), bad)[3] == 0
+
+
+def test_logs_bloom(ctx, oracle, golden):
+    """row N3: Receipt.calculateLogsBloom for a whole block (src/types/receipt.zig:37-63)"""
+    import numpy as np
+    from phant_b200.host import Log, calculate_logs_blooms
+    g = golden("logs_bloom_kat.json")
+    logs = [Log(bytes.fromhex(a), [bytes.fromhex(t) for t in ts]) for a, ts in g["logs"]]
+    blooms, block = calculate_logs_blooms(ctx, [logs, [], logs[:1]])
+    assert blooms[0].hex() == g["bloom"] and blooms[1] == bytes(256)
+    assert block == bytes(a | b for a, b in zip(blooms[0], blooms[2]))
+    # many receipts vs the oracle
+    rng = np.random.default_rng(4)
+    receipts, items, own = [], [], []
+    for r in range(500):
+        ls = []
+        for _ in range(int(rng.integers(0, 6))):
+            lg = Log(rng.integers(0, 256, 20, dtype=np.uint8).tobytes(), [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(int(rng.integers(0, 5)))])
+            ls.append(lg)
+            items.append(lg.address); own.append(r)
+            for t in lg.topics:
+                items.append(t); own.append(r)
+        receipts.append(ls)
+    blooms, block = calculate_logs_blooms(ctx, receipts)
+    want = oracle.logs_bloom(items, own, 500)
+    assert all(blooms[i] == want[i].tobytes() for i in range(500))
+    assert block == np.bitwise_or.reduce(want, axis=0).tobytes()

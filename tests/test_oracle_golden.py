@@ -122,3 +122,15 @@ def test_secure_trie_equals_compiled_evmone(oracle):
                                 v.ctypes.data_as(oracle_lib.u8p), voff.ctypes.data_as(oracle_lib.u64p), C.c_uint64(n),
                                 out.ctypes.data_as(oracle_lib.u8p))
         assert oracle.mptize(list(zip(keys, vals))) == out.tobytes(), n
+
+
+def test_logs_bloom_reference_vector(oracle, golden):
+    """Receipt.addToBloom (src/types/receipt.zig:50-63): the three-log receipt of
+    evmone/test/unittests/state_mpt_hash_test.cpp:118-190 and its on-chain logsBloom."""
+    g = golden("logs_bloom_kat.json")
+    items, own = [], []
+    for addr, topics in g["logs"]:
+        items.append(bytes.fromhex(addr)); own.append(0)
+        for t in topics:
+            items.append(bytes.fromhex(t)); own.append(0)
+    assert oracle.logs_bloom(items, own, 1)[0].tobytes().hex() == g["bloom"]
