@@ -1,0 +1,125 @@
+//! gpu.zig -- Zig binding of libphantgpu.so (include/phant_gpu.h) for phant.
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Zig toolchain.  It follows the patterns phant
+//! already uses for evmone (`@cImport` + `callconv(.C)`, src/blockchain/vm.zig:1-3) and is kept in step with
+//! host/phant_host.hpp, which binds the same symbols and is compiled and run by tests/test_gpu_host_cpp.py.
+//! Drop it at src/gpu/gpu.zig and add the build.zig lines of INTEGRATION.md section 1.
+const std = @import("std");
+const c = @cImport({
+    @cInclude("phant_gpu.h");
+});
+const types = @import("../types/types.zig");
+const mpt = @import("../mpt/mpt.zig");
+const Allocator = std.mem.Allocator;
+const Hash32 = types.Hash32;
+
+pub const Error = error{ GpuBackend, GpuUnavailable, OutOfMemory };
+
+pub const ProofStatus = enum(u8) { reject = 0, present = 1, absent = 2 };
+
+pub const Gpu = struct {
+    ctx: *c.phant_gpu_ctx,
+
+    /// One context per worker thread (contexts are not re-entrant; src/main.zig:143-149 runs handlers on httpz workers).
+    pub fn init(device: i32) Error!Gpu {
+        if (c.phant_gpu_abi_version() != c.PHANT_GPU_ABI_VERSION) return error.GpuUnavailable;
+        var cfg = std.mem.zeroes(c.phant_gpu_config);
+        cfg.device = device;
+        var ctx: ?*c.phant_gpu_ctx = null;
+        if (c.phant_gpu_create(&ctx, &cfg) != 0) return error.GpuUnavailable; // no CUDA device: the caller keeps its CPU path
+        return .{ .ctx = ctx.? };
+    }
+
+    pub fn deinit(self: *Gpu) void {
+        c.phant_gpu_destroy(self.ctx);
+    }
+
+    /// hasher.keccak256 (src/crypto/hasher.zig:4-8) for many inputs: message i = msgs[off[i]..off[i+1]).
+    pub fn keccak256Batch(self: *Gpu, msgs: []const u8, off: []const u64, out: []Hash32) Error!void {
+        std.debug.assert(off.len == out.len + 1);
+        if (c.phant_gpu_keccak256_batch(self.ctx, msgs.ptr, off.ptr, out.len, @ptrCast(out.ptr)) != 0) return error.GpuBackend;
+    }
+
+    /// == mpt.mptize (src/mpt/mpt.zig:38-45).  `list` sorted by key, as the reference asserts.
+    pub fn mptize(self: *Gpu, arena: Allocator, list: []const mpt.KeyVal) Error!Hash32 {
+        var keys = std.ArrayList(u8).init(arena);
+        var vals = std.ArrayList(u8).init(arena);
+        var key_off = try arena.alloc(u32, list.len + 1);
+        var val_off = try arena.alloc(u64, list.len + 1);
+        key_off[0] = 0;
+        val_off[0] = 0;
+        for (list, 0..) |kv, i| {
+            var j: usize = 0;
+            while (j + 1 < kv.nibbles.len) : (j += 2) try keys.append((kv.nibbles[j] << 4) | kv.nibbles[j + 1]); // KeyVal.init always makes nibble pairs
+            try vals.appendSlice(kv.value);
+            key_off[i + 1] = @intCast(keys.items.len);
+            val_off[i + 1] = vals.items.len;
+        }
+        var root: Hash32 = undefined;
+        if (c.phant_gpu_mpt_root(self.ctx, keys.items.ptr, key_off.ptr, vals.items.ptr, val_off.ptr, list.len, &root) != 0) return error.GpuBackend;
+        return root;
+    }
+
+    /// The body of the missing StateDB.root() (hook: src/blockchain/blockchain.zig:83-85).
+    pub fn stateRoot(self: *Gpu, accounts: *const c.phant_gpu_accounts) Error!Hash32 {
+        var root: Hash32 = undefined;
+        if (c.phant_gpu_state_root(self.ctx, accounts, &root) != 0) return error.GpuBackend;
+        return root;
+    }
+
+    /// The body of the TODO at src/engine_api/execution_payload.zig:177-178.  Accept / reject is data.
+    pub fn verifyProofs(self: *Gpu, batch: *const c.phant_gpu_proof_batch, accept_bitmap: []u64, status: ?[]u8) Error!void {
+        std.debug.assert(accept_bitmap.len * 64 >= batch.n_proofs);
+        const st: ?[*]u8 = if (status) |s| s.ptr else null;
+        if (c.phant_gpu_verify_proofs(self.ctx, batch, accept_bitmap.ptr, st, null, null) != 0) return error.GpuBackend;
+    }
+
+    /// Receipt.calculateLogsBloom (src/types/receipt.zig:37-48) for all receipts of a block.
+    pub fn logsBlooms(self: *Gpu, items: []const u8, item_off: []const u64, bloom_of_item: []const u32, blooms: []types.LogsBloom) Error!void {
+        if (c.phant_gpu_logs_bloom(self.ctx, items.ptr, item_off.ptr, bloom_of_item.ptr, bloom_of_item.len, blooms.len, @ptrCast(blooms.ptr)) != 0)
+            return error.GpuBackend;
+    }
+};
+
+/// Flatten phant's StateDB (src/state/statedb.zig:16-30) into the SoA the library takes and return the state root.
+pub fn stateDbRoot(gpu: *Gpu, arena: Allocator, statedb: anytype) Error!Hash32 {
+    var addr = std.ArrayList(u8).init(arena);
+    var nonce = std.ArrayList(u64).init(arena);
+    var balance = std.ArrayList(u8).init(arena);
+    var code = std.ArrayList(u8).init(arena);
+    var code_off = std.ArrayList(u64).init(arena);
+    var slot_keys = std.ArrayList(u8).init(arena);
+    var slot_vals = std.ArrayList(u8).init(arena);
+    var slot_off = std.ArrayList(u64).init(arena);
+    try code_off.append(0);
+    try slot_off.append(0);
+    var it = statedb.db.iterator();
+    while (it.next()) |entry| {
+        try addr.appendSlice(&entry.key_ptr.*);
+        try nonce.append(entry.value_ptr.nonce);
+        var be: [32]u8 = undefined;
+        std.mem.writeInt(u256, &be, entry.value_ptr.balance, .big);
+        try balance.appendSlice(&be);
+        try code.appendSlice(entry.value_ptr.code);
+        try code_off.append(code.items.len);
+        var sit = entry.value_ptr.storage.iterator();
+        while (sit.next()) |s| {
+            std.mem.writeInt(u256, &be, s.key_ptr.*, .big);
+            try slot_keys.appendSlice(&be);
+            try slot_vals.appendSlice(&s.value_ptr.*);
+        }
+        try slot_off.append(slot_keys.items.len / 32);
+    }
+    const table = c.phant_gpu_accounts{
+        .n_accounts = nonce.items.len,
+        .addr20 = addr.items.ptr,
+        .nonce = nonce.items.ptr,
+        .balance32 = balance.items.ptr,
+        .code = code.items.ptr,
+        .code_off = code_off.items.ptr,
+        .slot_keys32 = slot_keys.items.ptr,
+        .slot_vals32 = slot_vals.items.ptr,
+        .slot_off = slot_off.items.ptr,
+    };
+    return gpu.stateRoot(&table);
+}
