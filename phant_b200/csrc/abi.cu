@@ -37,6 +37,9 @@ int DevBuf::reserve(phant_gpu_ctx* ctx, size_t bytes)
     cudaError_t e = cudaMalloc(&ptr, want);
     if (e != cudaSuccess) { want = bytes + 256; e = cudaMalloc(&ptr, want); }
     if (e != cudaSuccess) { ptr = nullptr; return ctx->fail(e, "cudaMalloc", __FILE__, __LINE__); }
+    // zero once per (re)allocation: kernels read whole aligned words / 16-byte windows, i.e. up to 15 bytes past the
+    // last message byte; those bytes are masked off, but they should not be uninitialised memory
+    cudaMemset(ptr, 0, want);
     cap = want;
     return 0;
 }

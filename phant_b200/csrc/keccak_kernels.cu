@@ -50,6 +50,12 @@ __device__ __forceinline__ uint32_t summarize_node(const uint8_t* p, uint32_t le
         hdr = 1 + n;
     }
     if (hdr + pay != len) return 0;
+    if (len == 532) { // the full branch (16 hashed children): 17 independent byte probes instead of a dependent scan
+        uint32_t ok = p[531] == 0x80;
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) ok &= p[3 + 33 * i] == 0xa0;
+        if (ok) return (0xffffu << 8) | (3u << 2) | 1u;
+    }
     uint32_t o = hdr, mask = 0;
 #pragma unroll 1
     for (uint32_t i = 0; i < 16; ++i) {

@@ -994,6 +994,123 @@ __global__ void shift4_kernel(const uint32_t* __restrict__ in, uint64_t n, uint3
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) out[k] = in[k] >> 4;
 }
 
+// ---- fused frontier kernels: encode in shared memory, hash, store -- one launch per level, no arena, no host sync ----
+constexpr int FR_SLOT = 560;  // same geometry as the staged Keccak kernel's slots (16 x 35)
+constexpr int FR_WARPS = 4;
+constexpr int FR_SMEM = FR_WARPS * 32 * FR_SLOT + 16;
+
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+// byte stream -> aligned 32-bit shared-memory words; FILL (bytes pending in acc) is a compile-time constant everywhere
+template <int FILL>
+__device__ __forceinline__ void push_word(uint32_t& sa, uint32_t& acc, uint32_t h)
+{
+    if constexpr (FILL == 0) { sts32(sa, h); sa += 4; }
+    else { sts32(sa, acc | (h << (8 * FILL))); sa += 4; acc = h >> (32 - 8 * FILL); }
+}
+template <int S>
+__device__ __forceinline__ void push_child(uint32_t& sa, uint32_t& acc, const uint4 a, const uint4 b)
+{
+    // before child S the stream holds 3 + 33*S bytes: FILL = (3 + S) % 4; the 0xa0 marker goes first
+    constexpr int F0 = (3 + S) % 4;
+    if constexpr (F0 == 3) { sts32(sa, acc | (0xa0u << 24)); sa += 4; acc = 0; }
+    else acc |= 0xa0u << (8 * F0);
+    constexpr int F = (F0 + 1) % 4;
+    push_word<F>(sa, acc, a.x); push_word<F>(sa, acc, a.y); push_word<F>(sa, acc, a.z); push_word<F>(sa, acc, a.w);
+    push_word<F>(sa, acc, b.x); push_word<F>(sa, acc, b.y); push_word<F>(sa, acc, b.z); push_word<F>(sa, acc, b.w);
+}
+
+// Re-hash the dirty branch nodes of one level: parent p = parents[i] (i < *count), children = child_level[16p .. 16p+16).
+// Each thread writes the 532-byte encoding f9 0211 | 16 x (a0 hash) | 80 (mpt.zig:218-247) into its shared-memory slot as
+// aligned words, absorbs it with the product sponge, and stores the digest at level[p].
+__global__ void __launch_bounds__(FR_WARPS * 32)
+frontier_branch_kernel(const uint8_t* __restrict__ child_level, const uint32_t* __restrict__ parents, const uint32_t* __restrict__ count_ptr,
+                       uint32_t bound, uint8_t* __restrict__ level)
+{
+    extern __shared__ __align__(16) uint8_t fr_smem[];
+    const uint32_t slot = (uint32_t)__cvta_generic_to_shared(fr_smem) + threadIdx.x * FR_SLOT;
+    uint32_t count = *count_ptr;
+    if (count > bound) count = bound;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t p = parents[i];
+        const uint4* ch = reinterpret_cast<const uint4*>(child_level + 512ull * p);
+        uint32_t sa = slot, acc = 0x1102f9u; // f9 02 11 pending (FILL = 3)
+#define PC(S) push_child<S>(sa, acc, ch[2 * S], ch[2 * S + 1]);
+        PC(0) PC(1) PC(2) PC(3) PC(4) PC(5) PC(6) PC(7) PC(8) PC(9) PC(10) PC(11) PC(12) PC(13) PC(14) PC(15)
+#undef PC
+        // after 16 children: 3 + 33*16 = 531 bytes, FILL = 3: the empty value 0x80 completes the last word
+        sts32(sa, acc | (0x80u << 24));
+        uint64_t st[25];
+#pragma unroll
+        for (int k = 0; k < 25; ++k) st[k] = 0;
+        absorb_full_smem<2>(st, slot);
+        absorb_full_smem<2>(st, slot + 136);
+        absorb_full_smem<2>(st, slot + 272);
+        absorb_final_smem<2>(st, slot + 408, 532 - 408);
+        uint4* o = reinterpret_cast<uint4*>(level + 32ull * p);
+        o[0] = make_uint4((uint32_t)st[0], (uint32_t)(st[0] >> 32), (uint32_t)st[1], (uint32_t)(st[1] >> 32));
+        o[1] = make_uint4((uint32_t)st[2], (uint32_t)(st[2] >> 32), (uint32_t)st[3], (uint32_t)(st[3] >> 32));
+    }
+}
+
+// Dirty leaves: rlp([hp(key nibbles [depth, 64), leaf), value]) built in the slot, hashed, stored at the leaf's position.
+// Values up to FR_SLOT - 48 bytes (the caller checks); one thread per leaf.
+__global__ void __launch_bounds__(FR_WARPS * 32)
+frontier_leaf_kernel(const uint8_t* __restrict__ keys32, const uint8_t* __restrict__ vals, const uint32_t* __restrict__ val_off, uint32_t n,
+                     uint32_t depth, uint8_t* __restrict__ leaf_level, uint32_t* __restrict__ pos_out)
+{
+    extern __shared__ __align__(16) uint8_t fr_smem[];
+    const uint32_t slot = (uint32_t)__cvta_generic_to_shared(fr_smem) + threadIdx.x * FR_SLOT;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint8_t* key = keys32 + 32ull * k;
+        uint32_t pos = 0;
+        for (uint32_t i = 0; i < depth; ++i) pos = pos * 16 + ((i & 1) ? (key[i >> 1] & 15u) : (key[i >> 1] >> 4));
+        pos_out[k] = pos;
+        const uint32_t cnt = 64 - depth, hpn = 1 + cnt / 2;
+        const uint32_t vl = val_off[k + 1] - val_off[k];
+        const uint8_t* v = vals + val_off[k];
+        const uint32_t s_hp = hpn == 1 ? 1 : 1 + hpn, s_v = (uint32_t)str_size(vl, vl ? v[0] : 0);
+        const uint32_t payload = s_hp + s_v;
+        uint32_t sa = slot;
+        if (payload <= 55) { sts8(sa++, 0xc0 + payload); }
+        else if (payload < 256) { sts8(sa++, 0xf8); sts8(sa++, payload); }
+        else { sts8(sa++, 0xf9); sts8(sa++, payload >> 8); sts8(sa++, payload & 255); }
+        if (hpn > 1) sts8(sa++, 0x80 + hpn);
+        uint32_t i = depth;
+#define KN(j) (((j) & 1) ? (key[(j) >> 1] & 15u) : (key[(j) >> 1] >> 4))
+        if (cnt & 1) { sts8(sa++, 0x30 | KN(i)); ++i; } else sts8(sa++, 0x20);
+        for (; i < 64; i += 2) sts8(sa++, (KN(i) << 4) | KN(i + 1));
+#undef KN
+        if (s_v > vl) {
+            if (vl <= 55) sts8(sa++, 0x80 + vl);
+            else if (vl < 256) { sts8(sa++, 0xb8); sts8(sa++, vl); }
+            else { sts8(sa++, 0xb9); sts8(sa++, vl >> 8); sts8(sa++, vl & 255); }
+        }
+        for (uint32_t b = 0; b < vl; ++b) sts8(sa++, v[b]);
+        const uint32_t len = sa - slot;
+        uint64_t st[25];
+#pragma unroll
+        for (int q = 0; q < 25; ++q) st[q] = 0;
+        uint32_t at = slot, rem = len;
+        while (rem >= 136) { absorb_full_smem<2>(st, at); at += 136; rem -= 136; }
+        absorb_final_smem<2>(st, at, rem);
+        uint4* o = reinterpret_cast<uint4*>(leaf_level + 32ull * pos);
+        o[0] = make_uint4((uint32_t)st[0], (uint32_t)(st[0] >> 32), (uint32_t)st[1], (uint32_t)(st[1] >> 32));
+        o[1] = make_uint4((uint32_t)st[2], (uint32_t)(st[2] >> 32), (uint32_t)st[3], (uint32_t)(st[3] >> 32));
+    }
+}
+
+// children (sorted, `*count` valid of `bound`) -> parents = children >> 4, the tail padded with the last valid value so
+// that a fixed-size Unique over `bound` items yields exactly the distinct parents without the host knowing `*count`
+__global__ void shift4_pad_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ count_ptr, uint32_t bound, uint32_t* __restrict__ out)
+{
+    uint32_t count = *count_ptr;
+    if (count > bound) count = bound;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < bound; k += gridDim.x * blockDim.x)
+        out[k] = count ? in[k < count ? k : count - 1] >> 4 : 0;
+}
+
 int ctrie_hash_level(phant_gpu_trie* t, uint32_t l, const uint32_t* d_parents, uint64_t cnt)
 {
     // re-hash `cnt` branch nodes of level l (positions d_parents) from level l+1
@@ -1078,9 +1195,13 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
     if (n_dirty == 0) return phant_gpu_trie_root(t, out_root);
     if (!keys32 || !val_off || n_dirty >= (1ull << 28)) return PHANT_GPU_E_INVALID;
     const uint8_t* d_keys = keys32; const uint8_t* d_vals = leaf_vals; const uint32_t* d_voff = val_off;
-    uint64_t vb = 0;
+    uint64_t vb = 0, max_val = ~0ull;
     if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS)) {
-        for (uint64_t i = 0; i < n_dirty; ++i) if (val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
+        max_val = 0;
+        for (uint64_t i = 0; i < n_dirty; ++i) {
+            if (val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
+            if ((uint64_t)(val_off[i + 1] - val_off[i]) > max_val) max_val = val_off[i + 1] - val_off[i];
+        }
         vb = val_off[n_dirty];
         if (vb && !leaf_vals) return PHANT_GPU_E_INVALID;
         RC(ctx->d_msgs.reserve(ctx, 32 * n_dirty + vb + 4 * (n_dirty + 1) + 256));
@@ -1097,7 +1218,55 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
         CU(cudaStreamSynchronize(s));
     }
     const uint32_t L = t->depth;
-    // ---- dirty leaves: encode, hash (batched Keccak), scatter into the leaf level ----
+    if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) && max_val <= FR_SLOT - 48) {
+        // ---- fused frontier path: one launch for the leaves, then per level shift/pad + unique + one hash launch; the only
+        // host synchronisation is the final read of the root ----
+        static bool attr = false;
+        if (!attr) {
+            CU(cudaFuncSetAttribute(frontier_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM));
+            CU(cudaFuncSetAttribute(frontier_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM));
+            attr = true;
+        }
+        RC(ctx->d_b0.reserve(ctx, 4 * n_dirty * 4 + 256));
+        uint32_t* pos = (uint32_t*)ctx->d_b0.ptr;
+        uint32_t* cur = pos + n_dirty;
+        uint32_t* tmp = cur + n_dirty;
+        uint32_t* uniq = tmp + n_dirty;
+        RC(ctx->d_b3.reserve(ctx, 64));
+        uint32_t* counts = (uint32_t*)ctx->d_b3.ptr; // counts[0] = valid entries of `cur`
+        const unsigned fr_grid = (unsigned)((n_dirty + FR_WARPS * 32 - 1) / (FR_WARPS * 32));
+        const unsigned fr_cap = (unsigned)keccak_num_sms(ctx->device) * 3;
+        frontier_leaf_kernel<<<fr_grid < fr_cap ? fr_grid : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(d_keys, d_vals, d_voff, (uint32_t)n_dirty, L, t->level[L], pos);
+        size_t temp = 0;
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, temp, (const uint32_t*)pos, cur, (int64_t)n_dirty, 0, 4 * (int)L, s));
+        RC(ctx->d_cub.reserve(ctx, temp));
+        CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub.ptr, temp, (const uint32_t*)pos, cur, (int64_t)n_dirty, 0, 4 * (int)L, s));
+        const uint32_t nd = (uint32_t)n_dirty;
+        CU(cudaMemcpyAsync(counts, &nd, 4, cudaMemcpyHostToDevice, s));
+        ctx->stats.launches += 2;
+        uint64_t bound = n_dirty;
+        for (int l = (int)L - 1; l >= 0; --l) {
+            shift4_pad_kernel<<<grid1d(ctx->device, bound, 256), 256, 0, s>>>(cur, counts, (uint32_t)bound, tmp);
+            size_t t2 = 0;
+            CU(cub::DeviceSelect::Unique(nullptr, t2, (const uint32_t*)tmp, uniq, counts, (int64_t)bound, s));
+            RC(ctx->d_cub.reserve(ctx, t2));
+            CU(cub::DeviceSelect::Unique(ctx->d_cub.ptr, t2, (const uint32_t*)tmp, uniq, counts, (int64_t)bound, s));
+            uint64_t level_nodes = 1;
+            for (int q = 0; q < l; ++q) level_nodes *= 16;
+            if (bound > level_nodes) bound = level_nodes; // a level cannot have more dirty nodes than nodes
+            const unsigned g = (unsigned)((bound + FR_WARPS * 32 - 1) / (FR_WARPS * 32));
+            frontier_branch_kernel<<<g < fr_cap ? g : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(t->level[l + 1], uniq, counts, (uint32_t)bound, t->level[l]);
+            ctx->stats.launches += 3;
+            uint32_t* x = cur; cur = uniq; uniq = x;
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out_root, t->level[0], 32, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += 32;
+        CU(cudaStreamSynchronize(s));
+        return PHANT_GPU_OK;
+    }
+    // ---- general path (device pointers, or leaf values too large for a staging slot):
+    // dirty leaves: encode, hash (batched Keccak), scatter into the leaf level ----
     RC(ctx->d_b0.reserve(ctx, 4 * n_dirty * 4 + 8 * (n_dirty + 2) * 2 + 32 * n_dirty + 256));
     uint32_t* pos = (uint32_t*)ctx->d_b0.ptr;
     uint32_t* pa = pos + n_dirty;

@@ -38,6 +38,18 @@ def keccak256_with_prefix(ctx, prefix, data):
     return keccak256(ctx, bytes(prefix) + bytes(data))
 
 
+def tx_hashes(ctx, encoded_txs):
+    """Tx.hash (src/types/transaction.zig:79-85) for a whole block: keccak256 of each encoded transaction
+    (type byte || rlp for typed ones), one batched call (row N4 of SURVEY.md 8f: the hashing half of sender recovery)."""
+    return keccak256_batch(ctx, encoded_txs)
+
+
+def addresses_from_pubkeys(ctx, pubkeys65):
+    """the last step of TxSigner.get_sender (src/signer/signer.zig:78): keccak256(pubkey[1..])[12..] for many
+    recovered public keys at once (the secp256k1 recovery itself stays on the CPU: a different kernel family)"""
+    return [h[12:] for h in keccak256_batch(ctx, [bytes(p)[1:] for p in pubkeys65])]
+
+
 class KeyVal:
     """mpt.zig:13-34"""
 

@@ -9,6 +9,8 @@ Sources (relative to /root/reference):
   keccak_kat.json      ethash/test/unittests/test_keccak.cpp:20-195   (text + per-length Keccak-256)
   mptize_kat.json      src/mpt/mpt.zig:326-385                          (7 roots; transcribed below)
   evmone_mpt_kat.json  evmone/test/unittests/state_mpt_test.cpp:20-333, state_mpt_hash_test.cpp:19-66
+  logs_bloom_kat.json  evmone/test/unittests/state_mpt_hash_test.cpp:118-190 (logs + on-chain bloom of one receipt)
+  tx_hash_kat.json     src/types/transaction.zig:275-314 (three mainnet transactions and their hashes)
   fixture_states.json.gz
                        src/tests/fixtures/**.json: `pre` vs genesisBlockHeader.stateRoot, `postState` vs the
                        last valid block's blockHeader.stateRoot, and per valid block the raw transaction /
@@ -143,6 +145,15 @@ def evmone_kat():
                                  "topologies": groups, "examples": examples, "states": states})
 
 
+# ---------------------------------------------------------------- tx hashes (src/types/transaction.zig:275-314)
+def tx_hash_kat():
+    src = open(f"{REF}/src/types/transaction.zig").read()
+    cases = re.findall(r'\.rlp_encoded = "([0-9a-f]+)",\s*(?://\s*)?\.expected_hash = "([0-9a-f]{64})"', src)
+    assert len(cases) == 3, len(cases)  # legacy, EIP-2930 (commented out in the reference: a zig-rlp limitation), EIP-1559
+    dump("tx_hash_kat.json", {"source": "src/types/transaction.zig:275-314 (Tx.hash = keccak256 of the encoded transaction, :79-85)",
+                              "cases": [{"encoded": e, "hash": h} for e, h in cases]})
+
+
 # ---------------------------------------------------------------- fixtures
 def rlp_decode(b, pos=0):
     """-> (item, next_pos); item is bytes or list.  For list items also keep the raw encoding."""
@@ -225,4 +236,5 @@ if __name__ == "__main__":
     keccak_kat()
     mptize_kat()
     evmone_kat()
+    tx_hash_kat()
     fixtures()

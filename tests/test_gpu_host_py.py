@@ -116,3 +116,12 @@ def test_logs_bloom(ctx, oracle, golden):
     want = oracle.logs_bloom(items, own, 500)
     assert all(blooms[i] == want[i].tobytes() for i in range(500))
     assert block == np.bitwise_or.reduce(want, axis=0).tobytes()
+
+
+def test_tx_hashes_and_addresses(ctx, oracle, golden):
+    """row N4 (hashing half): Tx.hash for a block of transactions and address = keccak(pubkey[1:])[12:]"""
+    from phant_b200.host import addresses_from_pubkeys, tx_hashes
+    cases = golden("tx_hash_kat.json")["cases"]
+    assert [h.hex() for h in tx_hashes(ctx, [bytes.fromhex(c["encoded"]) for c in cases])] == [c["hash"] for c in cases]
+    pubs = [bytes([4]) + bytes([i]) * 64 for i in range(40)]
+    assert addresses_from_pubkeys(ctx, pubs) == [oracle.keccak256(p[1:])[12:] for p in pubs]

@@ -134,3 +134,9 @@ def test_logs_bloom_reference_vector(oracle, golden):
         for t in topics:
             items.append(bytes.fromhex(t)); own.append(0)
     assert oracle.logs_bloom(items, own, 1)[0].tobytes().hex() == g["bloom"]
+
+
+def test_tx_hash_reference_vectors(oracle, golden):
+    """src/types/transaction.zig:275-314: three mainnet transactions (legacy, EIP-2930, EIP-1559)."""
+    for c in golden("tx_hash_kat.json")["cases"]:
+        assert oracle.keccak256(bytes.fromhex(c["encoded"])).hex() == c["hash"]
