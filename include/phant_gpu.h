@@ -93,6 +93,13 @@ int phant_gpu_keccak256_batch(phant_gpu_ctx* ctx, const uint8_t* msgs, const uin
 int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const uint32_t* key_off, const uint8_t* vals,
                        const uint64_t* val_off, uint64_t n, uint8_t out_root[32]);
 
+/* M (batched) -- many independent tries in one call: trie t holds items [seg_off[t], seg_off[t+1]) of the CSR arrays,
+ * each segment sorted like a single mptize input.  All tries are built together as one forest (one set of launches
+ * whatever n_tries is): e.g. the transaction / receipt / withdrawal tries (src/blockchain/blockchain.zig:200-203)
+ * of a whole range of blocks.  out_roots = n_tries * 32 bytes; an empty segment gives empty_mpt_root. */
+int phant_gpu_mpt_roots(phant_gpu_ctx* ctx, const uint8_t* keys, const uint32_t* key_off, const uint8_t* vals, const uint64_t* val_off,
+                        const uint32_t* seg_off, uint64_t n_tries, uint8_t* out_roots);
+
 /* S -- state root of a flat account table: the body of the missing StateDB.root()
  * (hook: src/blockchain/blockchain.zig:83-85; data model src/state/statedb.zig:16-30,
  * src/state/types.zig:7-33).  Trie contents as in evmone/test/state/mpt_hash.cpp:15-36:

@@ -38,8 +38,10 @@ int DevBuf::reserve(phant_gpu_ctx* ctx, size_t bytes)
     if (e != cudaSuccess) { want = bytes + 256; e = cudaMalloc(&ptr, want); }
     if (e != cudaSuccess) { ptr = nullptr; return ctx->fail(e, "cudaMalloc", __FILE__, __LINE__); }
     // zero once per (re)allocation: kernels read whole aligned words / 16-byte windows, i.e. up to 15 bytes past the
-    // last message byte; those bytes are masked off, but they should not be uninitialised memory
-    cudaMemset(ptr, 0, want);
+    // last message byte; those bytes are masked off, but they should not be uninitialised memory.  On the context's
+    // stream, so that it is ordered before everything that fills the buffer (the stream is non-blocking: a memset on
+    // the legacy stream would race with it).
+    cudaMemsetAsync(ptr, 0, want, ctx->stream);
     cap = want;
     return 0;
 }

@@ -568,6 +568,54 @@ extern "C" int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const
     return PHANT_GPU_OK;
 }
 
+extern "C" int phant_gpu_mpt_roots(phant_gpu_ctx* ctx, const uint8_t* keys, const uint32_t* key_off, const uint8_t* vals,
+                                   const uint64_t* val_off, const uint32_t* seg_off, uint64_t n_tries, uint8_t* out_roots)
+{
+    if (!ctx || (n_tries && (!seg_off || !out_roots))) return PHANT_GPU_E_INVALID;
+    if (n_tries == 0) return PHANT_GPU_OK;
+    if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) return PHANT_GPU_E_INVALID; // the batched form takes host arrays
+    if (n_tries >= (1ull << 30)) return PHANT_GPU_E_INVALID;
+    for (uint64_t t = 0; t < n_tries; ++t) if (seg_off[t + 1] < seg_off[t]) return PHANT_GPU_E_INVALID;
+    if (seg_off[0] != 0) return PHANT_GPU_E_INVALID;
+    const uint64_t n = seg_off[n_tries];
+    if (n >= (1ull << 30) || (n && (!key_off || !val_off))) return PHANT_GPU_E_INVALID;
+    for (uint64_t i = 0; i < n; ++i)
+        if (key_off[i + 1] < key_off[i] || val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
+    const uint64_t kb = n ? key_off[n] : 0, vb = n ? val_off[n] : 0;
+    if ((kb && !keys) || (vb && !vals)) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // segment id of every key (the sortedness check must not compare across tries)
+    std::vector<uint32_t> seg_of_key(n ? n : 1);
+    for (uint64_t t = 0; t < n_tries; ++t)
+        for (uint32_t i = seg_off[t]; i < seg_off[t + 1]; ++i) seg_of_key[i] = (uint32_t)t;
+    RC(ctx->d_msgs.reserve(ctx, kb + vb + 128));
+    RC(ctx->d_off.reserve(ctx, 4 * (n + 1) + 8 * (n + 1) + 16));
+    RC(ctx->d_first.reserve(ctx, 4 * (n_tries + 1) + 4 * (n + 1) + 16));
+    RC(ctx->d_roots.reserve(ctx, 32 * n_tries));
+    uint8_t* dk = (uint8_t*)ctx->d_msgs.ptr;
+    uint8_t* dv = dk + ((kb + 63) & ~63ull);
+    uint64_t* dvo = (uint64_t*)ctx->d_off.ptr;
+    uint32_t* dko = (uint32_t*)(dvo + (n + 1));
+    uint32_t* dseg = (uint32_t*)ctx->d_first.ptr;
+    uint32_t* dsok = dseg + (n_tries + 1);
+    static const uint32_t zero_off[2] = {0, 0};
+    static const uint64_t zero_off64[2] = {0, 0};
+    if (kb) CU(cudaMemcpyAsync(dk, keys, kb, cudaMemcpyHostToDevice, s));
+    if (vb) CU(cudaMemcpyAsync(dv, vals, vb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dko, n ? key_off : zero_off, 4 * (n + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dvo, n ? val_off : zero_off64, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dseg, seg_off, 4 * (n_tries + 1), cudaMemcpyHostToDevice, s));
+    if (n) CU(cudaMemcpyAsync(dsok, seg_of_key.data(), 4 * n, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s)); // seg_of_key is a local vector: the copy must finish before it goes out of scope
+    ctx->stats.h2d_bytes += kb + vb + 16 * (n + 1) + 4 * (n_tries + 1);
+    RC(ctx->build_forest(dk, dko, dv, dvo, (uint32_t)n, dseg, (uint32_t)n_tries, dsok, (uint8_t*)ctx->d_roots.ptr));
+    CU(cudaMemcpyAsync(out_roots, ctx->d_roots.ptr, 32 * n_tries, cudaMemcpyDeviceToHost, s));
+    ctx->stats.d2h_bytes += 32 * n_tries;
+    CU(cudaStreamSynchronize(s));
+    return PHANT_GPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // S: state root
 // ------------------------------------------------------------------------------------------------

@@ -50,7 +50,7 @@ class TrieDesc(C.Structure):
 EXPORTS = [
     "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_set_stream", "phant_gpu_strerror",
     "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
-    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_state_root", "phant_gpu_verify_proofs",
+    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_verify_proofs",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
 ]
@@ -82,6 +82,7 @@ def _lib():
     L.phant_gpu_synchronize.argtypes = [vp]
     L.phant_gpu_keccak256_batch.argtypes = [vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_mpt_root.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp]
+    L.phant_gpu_mpt_roots.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_state_root.argtypes = [vp, C.POINTER(Accounts), vp]
     L.phant_gpu_verify_proofs.argtypes = [vp, C.POINTER(ProofBatch), vp, vp, vp, vp]
     L.phant_gpu_logs_bloom.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64, vp]
@@ -162,6 +163,12 @@ class Context:
         out = np.zeros(32, np.uint8)
         self._chk(_lib().phant_gpu_mpt_root(self._h, _ptr(keys), _ptr(key_off), _ptr(vals), _ptr(val_off), n, _ptr(out)), "mpt_root")
         return out.tobytes()
+
+    def mpt_roots(self, keys, key_off, vals, val_off, seg_off, n_tries):
+        out = np.zeros((max(n_tries, 1), 32), np.uint8)
+        self._chk(_lib().phant_gpu_mpt_roots(self._h, _ptr(keys), _ptr(key_off), _ptr(vals), _ptr(val_off), _ptr(seg_off), n_tries, _ptr(out)),
+                  "mpt_roots")
+        return [out[i].tobytes() for i in range(n_tries)]
 
     # S
     def state_root(self, n, addr20, nonce, balance32, code, code_off, slot_keys32, slot_vals32, slot_off):

@@ -74,6 +74,37 @@ def mptize(ctx, keyvals):
     return ctx.mpt_root(keys, koff, vals, voff, len(keyvals))
 
 
+def mptize_many(ctx, lists):
+    """many independent mptize calls as ONE forest build (phant_gpu_mpt_roots): lists = [[KeyVal, ...], ...]"""
+    flat = [kv for lst in lists for kv in lst]
+    keys, koff = _csr([kv.key_bytes() for kv in flat], np.uint32)
+    vals, voff = _csr([kv.value for kv in flat], np.uint64)
+    seg = np.zeros(len(lists) + 1, np.uint32)
+    seg[1:] = np.cumsum([len(lst) for lst in lists])
+    return ctx.mpt_roots(keys, koff, vals, voff, seg, len(lists))
+
+
+def _index_keyvals(encoded_items):
+    """blockchain.zig:214-232 key order"""
+    n = len(encoded_items)
+    kv, i = [], 0
+    while i + 1 < n and i + 1 != 0x80:
+        kv.append(KeyVal(bytes([i + 1]), encoded_items[i + 1]))
+        i += 1
+    if n > 0:
+        kv.append(KeyVal(b"\x80", encoded_items[0]))
+        i += 1
+    while i < n:
+        kv.append(KeyVal(_rlp_uint(i), encoded_items[i]))
+        i += 1
+    return kv
+
+
+def calculate_mpt_roots(ctx, item_lists):
+    """calculateMPTRoot for many lists at once (e.g. transactions / receipts / withdrawals of a range of blocks)"""
+    return mptize_many(ctx, [_index_keyvals(items) for items in item_lists])
+
+
 def _rlp_uint(i):
     if i == 0:
         return b"\x80"

@@ -125,3 +125,23 @@ def test_tx_hashes_and_addresses(ctx, oracle, golden):
     assert [h.hex() for h in tx_hashes(ctx, [bytes.fromhex(c["encoded"]) for c in cases])] == [c["hash"] for c in cases]
     pubs = [bytes([4]) + bytes([i]) * 64 for i in range(40)]
     assert addresses_from_pubkeys(ctx, pubs) == [oracle.keccak256(p[1:])[12:] for p in pubs]
+
+
+def test_batched_list_roots(ctx, golden, oracle):
+    """all 174 transaction / withdrawal tries of the fixtures in ONE forest build (phant_gpu_mpt_roots)"""
+    from phant_b200 import gpu
+    from phant_b200.host import KeyVal, calculate_mpt_roots, mptize_many
+    g = golden("fixture_states.json.gz")
+    lists, want = [], []
+    for t in g["tests"]:
+        for b in t["blocks"]:
+            lists.append([bytes.fromhex(x) for x in b["tx_values"]]); want.append(b["transactionsTrie"])
+            lists.append([bytes.fromhex(x) for x in b["wd_values"]]); want.append(b["withdrawalsRoot"])
+    got = calculate_mpt_roots(ctx, lists)
+    assert [r.hex() for r in got] == want and len(want) == 174
+    # the sortedness check is per trie: [b, a] in one trie is refused, [b] + [a] in two tries is fine
+    with pytest.raises(gpu.PhantGpuError):
+        mptize_many(ctx, [[KeyVal(b"\x02", b"x"), KeyVal(b"\x01", b"y")]])
+    two = mptize_many(ctx, [[KeyVal(b"\x02", b"x")], [KeyVal(b"\x01", b"y")], []])
+    assert two[0] == oracle.mptize([(b"\x02", b"x")]) and two[1] == oracle.mptize([(b"\x01", b"y")])
+    assert two[2].hex() == "56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"
