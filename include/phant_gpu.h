@@ -142,6 +142,24 @@ typedef struct {
 int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* in, uint64_t* accept_bitmap,
                             uint8_t* status, uint64_t* val_off, uint32_t* val_len);
 
+/* W -- witness given as an unordered SET of nodes (the shape of an execution witness: `state: [node, ...]`), not as
+ * one chain per key.  Every node is hashed once, a device hash table maps digest -> node, and each key is walked
+ * from its root resolving every hash reference through the table.  Same node rules as V (R1, R2, R3 without the
+ * chain-position clauses); status gets a fourth value: 3 = a node on the key's path is not in the set (incomplete
+ * witness).  accept bit = status 1 or 2.  Nodes not on any path are harmless. */
+typedef struct {
+    uint64_t n_nodes;
+    const uint8_t* nodes;
+    const uint64_t* node_off; /* n_nodes+1 */
+    uint64_t nodes_bytes;     /* = node_off[n_nodes] (device pointers: required; host pointers: derived) */
+    uint64_t n_keys;
+    const uint8_t* keys32;    /* n_keys*32 */
+    const uint8_t* roots32;   /* n_roots*32 */
+    uint64_t n_roots;         /* 1 (broadcast) or n_keys */
+} phant_gpu_witness;
+int phant_gpu_verify_witness(phant_gpu_ctx* ctx, const phant_gpu_witness* in, uint64_t* accept_bitmap, uint8_t* status,
+                             uint64_t* val_off, uint32_t* val_len);
+
 /* B -- logs blooms (row N3 of SURVEY.md 8f): Receipt.calculateLogsBloom / addToBloom
  * (src/types/receipt.zig:37-63) for many receipts at once.  items = the bloom inputs (log addresses 20 B, topics
  * 32 B, ...) CSR; bloom_of_item[i] says which of the n_blooms 2048-bit filters item i belongs to.  Each item is

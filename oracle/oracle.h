@@ -90,6 +90,11 @@ typedef struct {
 void oracle_verify_proofs(const oracle_proof_batch* in, uint64_t* accept_bitmap, uint8_t* status,
                           uint64_t* val_off, uint32_t* val_len, int threads);
 
+/* Bag verification: the witness is an unordered set of nodes (execution-witness shape); references are resolved by
+ * digest lookup.  status 0 reject, 1 present, 2 absent, 3 node missing from the bag.  See verify.c. */
+void oracle_verify_bag(const uint8_t* nodes, const uint64_t* node_off, uint64_t n_nodes, const uint8_t* keys32, uint64_t n_keys,
+                       const uint8_t* roots32, uint64_t n_roots, uint8_t* status, uint64_t* val_off, uint32_t* val_len, int threads);
+
 /* ---- complete-trie dirty-frontier update (config C4) ---- */
 typedef struct oracle_ctrie oracle_ctrie;
 /* depth = number of branch levels L (leaves = 16^L); untouched leaf hashes come from the PRNG. */

@@ -20,19 +20,46 @@
  */
 #include "oracle.h"
 #include "rlp.h"
+#include <stdlib.h>
 
-enum { ST_REJECT = 0, ST_PRESENT = 1, ST_ABSENT = 2 };
+enum { ST_REJECT = 0, ST_PRESENT = 1, ST_ABSENT = 2, ST_MISSING = 3 };
+
+/* Bag mode (oracle_verify_bag): the witness is an unordered SET of nodes (the shape of an execution witness), not a
+ * chain per key.  Same rules R1/R2/R3 with these changes: a hash reference is resolved by looking its 32 bytes up
+ * among the digests of the bag -- not found = ST_MISSING (the witness is incomplete; not accepted); terminals need
+ * not be "the last node" (there is no chain) and unused nodes are harmless. */
+typedef struct {
+    const uint8_t* digests; /* n * 32, digest of node i */
+    const uint32_t* sorted; /* node indices sorted by digest */
+    uint64_t n;
+} bag_index;
+
+static int64_t bag_find(const bag_index* b, const uint8_t h[32])
+{
+    uint64_t lo = 0, hi = b->n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) / 2;
+        int c = memcmp(b->digests + 32ull * b->sorted[mid], h, 32);
+        if (c == 0) return b->sorted[mid];
+        if (c < 0) lo = mid + 1; else hi = mid;
+    }
+    return -1;
+}
 
 static const uint8_t EMPTY_ROOT[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45,
                                        0xe6, 0x92, 0xc0, 0xf8, 0x6e, 0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c,
                                        0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
 
 static int verify_one(const uint8_t* nodes, const uint64_t* node_off, const uint64_t* node_index, uint64_t first, uint64_t last,
-                      const uint8_t* key32, const uint8_t* root32, uint64_t* voff, uint32_t* vlen)
+                      const uint8_t* key32, const uint8_t* root32, uint64_t* voff, uint32_t* vlen, const bag_index* bag)
 {
     *voff = 0;
     *vlen = 0;
-    if (first == last) return memcmp(root32, EMPTY_ROOT, 32) == 0 ? ST_ABSENT : ST_REJECT;
+    if (bag) { /* no chain: every "is this the last node" test passes, nothing is ever "left over" */
+        first = 0;
+        last = 1;
+        if (memcmp(root32, EMPTY_ROOT, 32) == 0) return ST_ABSENT;
+    } else if (first == last) return memcmp(root32, EMPTY_ROOT, 32) == 0 ? ST_ABSENT : ST_REJECT;
 
     uint8_t nib[64];
     for (int i = 0; i < 32; ++i) { nib[2 * i] = key32[i] >> 4; nib[2 * i + 1] = key32[i] & 15; }
@@ -47,7 +74,13 @@ static int verify_one(const uint8_t* nodes, const uint64_t* node_off, const uint
     int embedded = 0;
 
     for (;;) {
-        if (!embedded) {
+        if (!embedded && bag) {
+            const int64_t ni = bag_find(bag, expect);
+            if (ni < 0) return ST_MISSING;
+            cur = nodes + node_off[ni];
+            cur_len = node_off[ni + 1] - node_off[ni];
+            i = last; /* "we are at the last node" for every terminal test below */
+        } else if (!embedded) {
             if (i == last) return ST_REJECT; /* hash reference without a node to resolve it */
             const uint64_t ni = node_index ? node_index[i] : i; /* deduplicated witness: chains hold node indices */
             cur = nodes + node_off[ni];
@@ -151,7 +184,7 @@ void oracle_verify_proofs(const oracle_proof_batch* in, uint64_t* accept_bitmap,
             uint64_t vo;
             uint32_t vl;
             int st = verify_one(in->nodes, in->node_off, in->node_index, in->proof_first[p], in->proof_first[p + 1],
-                                in->keys32 + 32 * p, root, &vo, &vl);
+                                in->keys32 + 32 * p, root, &vo, &vl, NULL);
             if (status) status[p] = (uint8_t)st;
             if (val_off) val_off[p] = vo;
             if (val_len) val_len[p] = vl;
@@ -159,4 +192,37 @@ void oracle_verify_proofs(const oracle_proof_batch* in, uint64_t* accept_bitmap,
         }
         if (accept_bitmap) accept_bitmap[w] = word;
     }
+}
+
+/* qsort context (single-threaded use) */
+static const uint8_t* g_sort_digests;
+static int cmp_by_digest(const void* a, const void* b)
+{
+    return memcmp(g_sort_digests + 32ull * *(const uint32_t*)a, g_sort_digests + 32ull * *(const uint32_t*)b, 32);
+}
+
+/* Bag verification: nodes CSR (unordered set), n_keys keys, roots32 (n_roots == 1 or n_keys).  status: 0 reject (malformed
+ * node on the path), 1 present, 2 absent, 3 a node on the path is missing from the bag. */
+void oracle_verify_bag(const uint8_t* nodes, const uint64_t* node_off, uint64_t n_nodes, const uint8_t* keys32, uint64_t n_keys,
+                       const uint8_t* roots32, uint64_t n_roots, uint8_t* status, uint64_t* val_off, uint32_t* val_len, int threads)
+{
+    uint8_t* digests = malloc(32 * n_nodes + 32);
+    uint32_t* sorted = malloc(4 * n_nodes + 4);
+    oracle_keccak256_batch(nodes, node_off, n_nodes, digests, threads);
+    for (uint64_t i = 0; i < n_nodes; ++i) sorted[i] = (uint32_t)i;
+    g_sort_digests = digests;
+    qsort(sorted, n_nodes, 4, cmp_by_digest);
+    bag_index bag = {digests, sorted, n_nodes};
+    if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 64)
+    for (int64_t p = 0; p < (int64_t)n_keys; ++p) {
+        uint64_t vo;
+        uint32_t vl;
+        int st = verify_one(nodes, node_off, NULL, 0, 0, keys32 + 32 * p, roots32 + (n_roots == 1 ? 0 : 32 * p), &vo, &vl, &bag);
+        status[p] = (uint8_t)st;
+        if (val_off) val_off[p] = vo;
+        if (val_len) val_len[p] = vl;
+    }
+    free(digests);
+    free(sorted);
 }

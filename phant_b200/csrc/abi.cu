@@ -446,6 +446,69 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
 }
 
 // ------------------------------------------------------------------------------------------------
+// W: witness as a set of nodes
+// ------------------------------------------------------------------------------------------------
+extern "C" int phant_gpu_verify_witness(phant_gpu_ctx* ctx, const phant_gpu_witness* in, uint64_t* accept_bitmap, uint8_t* status,
+                                        uint64_t* val_off, uint32_t* val_len)
+{
+    if (!ctx || !in) return PHANT_GPU_E_INVALID;
+    const uint64_t nk = in->n_keys, nn = in->n_nodes;
+    if (nk == 0) return PHANT_GPU_OK;
+    if (!in->keys32 || !in->roots32 || (nn && !in->node_off) || (in->n_roots != 1 && in->n_roots != nk)) return PHANT_GPU_E_INVALID;
+    if (nn >= (1ull << 31)) return PHANT_GPU_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool dev = ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS;
+    const size_t bm_bytes = ((nk + 63) / 64) * 8;
+    uint64_t total = in->nodes_bytes;
+    const uint8_t* d_nodes = in->nodes; const uint64_t* d_noff = in->node_off; const uint8_t* d_keys = in->keys32; const uint8_t* d_roots = in->roots32;
+    uint64_t* d_bitmap = accept_bitmap; uint8_t* d_status = status; uint64_t* d_voff = val_off; uint32_t* d_vlen = val_len;
+    if (!dev) {
+        total = 0;
+        if (nn) { if (int rc = check_offsets_host(in->node_off, nn, &total)) return rc; }
+        if (total && !in->nodes) return PHANT_GPU_E_INVALID;
+        if (int rc = ctx->d_msgs.reserve(ctx, total + 64)) return rc;
+        if (int rc = ctx->d_off.reserve(ctx, 8 * (nn + 1))) return rc;
+        if (int rc = ctx->d_keys.reserve(ctx, 32 * nk)) return rc;
+        if (int rc = ctx->d_roots.reserve(ctx, 32 * in->n_roots)) return rc;
+        if (int rc = ctx->d_bitmap.reserve(ctx, bm_bytes)) return rc;
+        if (int rc = ctx->d_status.reserve(ctx, nk)) return rc;
+        if (val_off) if (int rc = ctx->d_voff.reserve(ctx, 8 * nk)) return rc;
+        if (val_len) if (int rc = ctx->d_vlen.reserve(ctx, 4 * nk)) return rc;
+        if (total) CU(cudaMemcpyAsync(ctx->d_msgs.ptr, in->nodes, total, cudaMemcpyHostToDevice, s));
+        static const uint64_t zero2[2] = {0, 0};
+        CU(cudaMemcpyAsync(ctx->d_off.ptr, nn ? in->node_off : zero2, 8 * (nn + 1), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(ctx->d_keys.ptr, in->keys32, 32 * nk, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(ctx->d_roots.ptr, in->roots32, 32 * in->n_roots, cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += total + 8 * (nn + 1) + 32 * nk + 32 * in->n_roots;
+        d_nodes = (const uint8_t*)ctx->d_msgs.ptr; d_noff = (const uint64_t*)ctx->d_off.ptr; d_keys = (const uint8_t*)ctx->d_keys.ptr;
+        d_roots = (const uint8_t*)ctx->d_roots.ptr; d_bitmap = (uint64_t*)ctx->d_bitmap.ptr; d_status = (uint8_t*)ctx->d_status.ptr;
+        d_voff = val_off ? (uint64_t*)ctx->d_voff.ptr : nullptr; d_vlen = val_len ? (uint32_t*)ctx->d_vlen.ptr : nullptr;
+    }
+    uint32_t capacity = 64;
+    while (capacity < 2 * nn) capacity <<= 1; // load factor <= 0.5
+    if (int rc = ctx->d_digests.reserve(ctx, 32 * nn + 32)) return rc;
+    if (int rc = ctx->d_summary.reserve(ctx, 4 * nn + 32)) return rc;
+    if (int rc = ctx->d_index.reserve(ctx, 4ull * capacity)) return rc;
+    if (int rc = ctx->hash_csr(d_nodes, d_noff, nn, total, (uint8_t*)ctx->d_digests.ptr, (uint32_t*)ctx->d_summary.ptr)) return rc;
+    CU(launch_bag_build(s, ctx->device, (const uint8_t*)ctx->d_digests.ptr, nn, (uint32_t*)ctx->d_index.ptr, capacity));
+    if (d_bitmap) CU(cudaMemsetAsync(d_bitmap, 0, bm_bytes, s));
+    ctx->time_begin(1);
+    CU(launch_walk_bag(s, ctx->device, nk, d_nodes, d_noff, d_keys, d_roots, in->n_roots, (const uint8_t*)ctx->d_digests.ptr,
+                       (const uint32_t*)ctx->d_summary.ptr, (const uint32_t*)ctx->d_index.ptr, capacity, d_bitmap, d_status, d_voff, d_vlen));
+    ctx->time_end();
+    ctx->stats.launches += 2;
+    if (!dev) {
+        if (accept_bitmap) { CU(cudaMemcpyAsync(accept_bitmap, d_bitmap, bm_bytes, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += bm_bytes; }
+        if (status) { CU(cudaMemcpyAsync(status, d_status, nk, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += nk; }
+        if (val_off) { CU(cudaMemcpyAsync(val_off, d_voff, 8 * nk, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += 8 * nk; }
+        if (val_len) { CU(cudaMemcpyAsync(val_len, d_vlen, 4 * nk, cudaMemcpyDeviceToHost, s)); ctx->stats.d2h_bytes += 4 * nk; }
+        CU(cudaStreamSynchronize(s));
+    }
+    return PHANT_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // B: logs blooms (src/types/receipt.zig:37-63)
 // ------------------------------------------------------------------------------------------------
 __global__ void bloom_set_kernel(const uint8_t* __restrict__ digests, const uint32_t* __restrict__ bloom_of_item, uint64_t n_items,

@@ -20,6 +20,11 @@ cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uin
                         const uint8_t* digests, const uint32_t* summary /*nullable*/, uint64_t* bitmap, uint8_t* status,
                         uint64_t* val_off, uint32_t* val_len);
 
+cudaError_t launch_bag_build(cudaStream_t s, int device, const uint8_t* digests, uint64_t n_nodes, uint32_t* table, uint32_t capacity);
+cudaError_t launch_walk_bag(cudaStream_t s, int device, uint64_t n_keys, const uint8_t* nodes, const uint64_t* node_off, const uint8_t* keys32,
+                            const uint8_t* roots32, uint64_t n_roots, const uint8_t* digests, const uint32_t* summary, const uint32_t* table,
+                            uint32_t capacity, uint64_t* bitmap, uint8_t* status, uint64_t* val_off, uint32_t* val_len);
+
 // synth.cu
 cudaError_t launch_synth_c2(cudaStream_t s, int device, uint64_t seed, uint64_t first_index, uint64_t n, uint32_t depth,
                             int corrupt, uint8_t* nodes, uint64_t* node_off, uint64_t* proof_first, uint8_t* keys32,

@@ -13,7 +13,15 @@
 namespace phant {
 namespace {
 
-enum { ST_REJECT = 0, ST_PRESENT = 1, ST_ABSENT = 2 };
+enum { ST_REJECT = 0, ST_PRESENT = 1, ST_ABSENT = 2, ST_MISSING = 3 };
+
+// Bag mode: the witness is an unordered set of nodes; a hash reference is resolved through an open-addressing table
+// keyed by the first 8 digest bytes (full 32-byte compare on hit).  table[slot] = node index or EMPTY.
+constexpr uint32_t BAG_EMPTY = 0xffffffffu;
+struct Bag {
+    const uint32_t* table;
+    uint32_t mask; // capacity - 1 (power of two)
+};
 
 struct Item {
     uint32_t is_list;
@@ -92,15 +100,37 @@ __constant__ uint8_t EMPTY_ROOT[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55,
                                        0xe6, 0x92, 0xc0, 0xf8, 0x6e, 0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c,
                                        0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
 
+__device__ __forceinline__ uint32_t bag_slot(const uint32_t (&e)[8], uint32_t mask)
+{
+    uint64_t h = ((uint64_t)e[1] << 32) | e[0];
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32; // the digest is uniform already; this only decorrelates from `mask`
+    return (uint32_t)h & mask;
+}
+__device__ uint32_t bag_find(const Bag& bag, const uint8_t* __restrict__ digests, const uint32_t (&expect)[8])
+{
+    uint32_t s = bag_slot(expect, bag.mask);
+    for (;;) {
+        const uint32_t idx = bag.table[s];
+        if (idx == BAG_EMPTY) return BAG_EMPTY;
+        if (eq32_aligned(digests + 32ull * idx, expect)) return idx;
+        s = (s + 1) & bag.mask;
+    }
+}
+
+template <bool BAG>
 __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
-                        const uint64_t* __restrict__ node_index, uint64_t first,
+                        const uint64_t* __restrict__ node_index, const Bag bag, uint64_t first,
                         uint64_t last, const uint8_t* __restrict__ key, const uint8_t* __restrict__ root,
                         const uint8_t* __restrict__ digests, const uint32_t* __restrict__ summary, uint64_t& voff, uint32_t& vlen)
 {
     voff = 0; vlen = 0;
     uint32_t expect[8];
     load32_aligned(root, expect);
-    if (first == last) return eq32_const(EMPTY_ROOT, expect) ? ST_ABSENT : ST_REJECT;
+    if (BAG) { // no chain: first/last only feed the "is this the last node" tests, which always pass
+        first = 0;
+        last = 1;
+        if (eq32_const(EMPTY_ROOT, expect)) return ST_ABSENT;
+    } else if (first == last) return eq32_const(EMPTY_ROOT, expect) ? ST_ABSENT : ST_REJECT;
 
     uint32_t pos = 0; // nibbles of the key consumed
     uint64_t i = first;
@@ -110,14 +140,22 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
 
     for (;;) {
         if (!embedded) {
-            if (i == last) return ST_REJECT; // R3: a hash reference needs a node
-            const uint64_t ni = node_index ? node_index[i] : i; // deduplicated witness: the chain holds node indices
+            uint64_t ni;
+            if (BAG) {
+                const uint32_t f = bag_find(bag, digests, expect);
+                if (f == BAG_EMPTY) return ST_MISSING; // the witness does not contain the node this reference names
+                ni = f;
+                i = last - 1; // so that ++i below leaves i == last: every terminal test sees "last node"
+            } else {
+                if (i == last) return ST_REJECT; // R3: a hash reference needs a node
+                ni = node_index ? node_index[i] : i; // deduplicated witness: the chain holds node indices
+            }
             const uint64_t o = node_off[ni];
             const uint64_t l = node_off[ni + 1] - o;
             if (l > 0xffffffffull) return ST_REJECT;
             cur = nodes + o;
             cur_len = (uint32_t)l;
-            if (!eq32_aligned(digests + 32 * ni, expect)) return ST_REJECT; // R1
+            if (!BAG && !eq32_aligned(digests + 32 * ni, expect)) return ST_REJECT; // R1 (bag: the lookup compared it)
             // fast path: the hash kernel already proved this node a simple branch (canonical 17-item list, children
             // empty or 32-byte hashes, empty value) and left the child mask: no parse, one 32-byte fetch
             const uint32_t sm = summary ? summary[ni] : 0;
@@ -220,8 +258,9 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
     }
 }
 
+template <bool BAG>
 __global__ void __launch_bounds__(128)
-walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
+walk_kernel(const Bag bag, uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
             const uint64_t* __restrict__ node_index, const uint64_t* __restrict__ proof_first, const uint8_t* __restrict__ keys32,
             const uint8_t* __restrict__ roots32, uint64_t n_roots, const uint8_t* __restrict__ digests,
             const uint32_t* __restrict__ summary, uint64_t* __restrict__ bitmap, uint8_t* __restrict__ status, uint64_t* __restrict__ val_off,
@@ -233,13 +272,13 @@ walk_kernel(uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t
         if (p < n_proofs) {
             uint64_t vo;
             uint32_t vl;
-            st = walk_one(nodes, node_off, node_index, proof_first[p], proof_first[p + 1], keys32 + 32 * p,
+            st = walk_one<BAG>(nodes, node_off, node_index, bag, BAG ? 0 : proof_first[p], BAG ? 0 : proof_first[p + 1], keys32 + 32 * p,
                           roots32 + (n_roots == 1 ? 0 : 32 * p), digests, summary, vo, vl);
             if (status) status[p] = (uint8_t)st;
             if (val_off) val_off[p] = vo;
             if (val_len) val_len[p] = vl;
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, st != ST_REJECT);
+        const uint32_t word = __ballot_sync(0xffffffffu, st == ST_PRESENT || st == ST_ABSENT); // missing node (3) is not an accept
         if (bitmap && (threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(bitmap)[p >> 5] = word;
     }
 }
@@ -255,8 +294,50 @@ cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uin
     uint64_t blocks = (n_proofs + 127) / 128;
     const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
     if (blocks > cap) blocks = cap;
-    walk_kernel<<<(unsigned)blocks, 128, 0, s>>>(n_proofs, nodes, node_off, node_index, proof_first, keys32, roots32, n_roots, digests, summary,
+    walk_kernel<false><<<(unsigned)blocks, 128, 0, s>>>(Bag{nullptr, 0}, n_proofs, nodes, node_off, node_index, proof_first, keys32, roots32, n_roots, digests, summary,
                                                  bitmap, status, val_off, val_len);
+    return cudaGetLastError();
+}
+
+// ---- bag mode: table build + walk ----
+namespace {
+__global__ void bag_insert_kernel(const uint8_t* __restrict__ digests, uint64_t n_nodes, uint32_t* __restrict__ table, uint32_t mask)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t e[8];
+        load32_aligned(digests + 32 * i, e);
+        uint32_t s = bag_slot(e, mask);
+        for (;;) {
+            const uint32_t prev = atomicCAS(&table[s], BAG_EMPTY, (uint32_t)i);
+            if (prev == BAG_EMPTY) break;
+            if (eq32_aligned(digests + 32ull * prev, e)) break; // the same node twice in the bag: one entry is enough
+            s = (s + 1) & mask;
+        }
+    }
+}
+} // namespace
+
+cudaError_t launch_bag_build(cudaStream_t s, int device, const uint8_t* digests, uint64_t n_nodes, uint32_t* table, uint32_t capacity)
+{
+    cudaError_t e = cudaMemsetAsync(table, 0xff, 4ull * capacity, s);
+    if (e != cudaSuccess || n_nodes == 0) return e;
+    uint64_t blocks = (n_nodes + 255) / 256;
+    const uint64_t cap = (uint64_t)keccak_num_sms(device) * 8;
+    if (blocks > cap) blocks = cap;
+    bag_insert_kernel<<<(unsigned)blocks, 256, 0, s>>>(digests, n_nodes, table, capacity - 1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_walk_bag(cudaStream_t s, int device, uint64_t n_keys, const uint8_t* nodes, const uint64_t* node_off, const uint8_t* keys32,
+                            const uint8_t* roots32, uint64_t n_roots, const uint8_t* digests, const uint32_t* summary, const uint32_t* table,
+                            uint32_t capacity, uint64_t* bitmap, uint8_t* status, uint64_t* val_off, uint32_t* val_len)
+{
+    if (n_keys == 0) return cudaSuccess;
+    uint64_t blocks = (n_keys + 127) / 128;
+    const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
+    if (blocks > cap) blocks = cap;
+    walk_kernel<true><<<(unsigned)blocks, 128, 0, s>>>(Bag{table, capacity - 1}, n_keys, nodes, node_off, nullptr, nullptr, keys32, roots32, n_roots,
+                                                      digests, summary, bitmap, status, val_off, val_len);
     return cudaGetLastError();
 }
 

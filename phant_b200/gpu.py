@@ -43,6 +43,11 @@ class ProofBatch(C.Structure):
                 ("nodes_bytes", C.c_uint64), ("node_index", C.c_void_p)]
 
 
+class Witness(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("nodes", C.c_void_p), ("node_off", C.c_void_p), ("nodes_bytes", C.c_uint64),
+                ("n_keys", C.c_uint64), ("keys32", C.c_void_p), ("roots32", C.c_void_p), ("n_roots", C.c_uint64)]
+
+
 class TrieDesc(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("depth", C.c_uint32), ("seed", C.c_uint64), ("reserved", C.c_uint64 * 4)]
 
@@ -50,7 +55,7 @@ class TrieDesc(C.Structure):
 EXPORTS = [
     "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_set_stream", "phant_gpu_strerror",
     "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
-    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_verify_proofs",
+    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
 ]
@@ -85,6 +90,7 @@ def _lib():
     L.phant_gpu_mpt_roots.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_state_root.argtypes = [vp, C.POINTER(Accounts), vp]
     L.phant_gpu_verify_proofs.argtypes = [vp, C.POINTER(ProofBatch), vp, vp, vp, vp]
+    L.phant_gpu_verify_witness.argtypes = [vp, C.POINTER(Witness), vp, vp, vp, vp]
     L.phant_gpu_logs_bloom.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64, vp]
     L.phant_gpu_trie_open.argtypes = [vp, C.POINTER(TrieDesc), C.POINTER(vp)]
     L.phant_gpu_trie_root.argtypes = [vp, vp]
@@ -185,6 +191,13 @@ class Context:
                        n_nodes, nodes_bytes, _ptr(node_index))
         self._chk(_lib().phant_gpu_verify_proofs(self._h, C.byref(b), _ptr(bitmap), _ptr(status), _ptr(val_off), _ptr(val_len)),
                   "verify_proofs")
+
+    # W
+    def verify_witness(self, n_nodes, nodes, node_off, n_keys, keys32, roots32, n_roots, bitmap=None, status=None, val_off=None,
+                       val_len=None, nodes_bytes=0):
+        w = Witness(n_nodes, _ptr(nodes), _ptr(node_off), nodes_bytes, n_keys, _ptr(keys32), _ptr(roots32), n_roots)
+        self._chk(_lib().phant_gpu_verify_witness(self._h, C.byref(w), _ptr(bitmap), _ptr(status), _ptr(val_off), _ptr(val_len)),
+                  "verify_witness")
 
     # B
     def logs_bloom(self, items, item_off, bloom_of_item, n_items, n_blooms, blooms):

@@ -192,6 +192,19 @@ def calculate_logs_blooms(ctx, receipts_logs):
     return [b.tobytes() for b in blooms[:n]], block.tobytes()
 
 
+def verify_witness_nodes(ctx, state_root, nodes, hashed_keys):
+    """execution_payload.zig:177-178 for a witness that is an unordered SET of trie nodes (`state: [node, ...]`):
+    -> status per key: 0 reject, 1 present, 2 absent, 3 node missing from the set"""
+    n = len(hashed_keys)
+    if n == 0:
+        return []
+    data, off = _csr(list(nodes), np.uint64)
+    keys = np.frombuffer(b"".join(hashed_keys), np.uint8)
+    status = np.zeros(n, np.uint8)
+    ctx.verify_witness(len(nodes), data, off, n, keys, np.frombuffer(bytes(state_root), np.uint8), 1, None, status, None, None)
+    return status.tolist()
+
+
 def verify_witness(ctx, state_root, proofs):
     """proofs: list of (hashed_key32, [node bytes, root first]).  Returns the status list (0 reject / 1 present /
     2 absent); execution_payload.zig:177-178 would refuse the payload unless none is 0."""

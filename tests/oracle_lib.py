@@ -191,6 +191,16 @@ class Oracle:
         self.lib.oracle_verify_proofs(C.byref(b), _p(bitmap, u64p), _p(status, u8p), _p(voff, u64p), _p(vlen, u32p), threads)
         return bitmap, status[:n], voff[:n], vlen[:n]
 
+    def verify_bag(self, nodes, node_off, keys32, roots32, threads=1):
+        n_nodes, n_keys = len(node_off) - 1, keys32.size // 32
+        status = np.zeros(max(n_keys, 1), np.uint8)
+        voff = np.zeros(max(n_keys, 1), np.uint64)
+        vlen = np.zeros(max(n_keys, 1), np.uint32)
+        self.lib.oracle_verify_bag.argtypes = [u8p, u64p, C.c_uint64, u8p, C.c_uint64, u8p, C.c_uint64, u8p, u64p, u32p, C.c_int]
+        self.lib.oracle_verify_bag(_p(np.ascontiguousarray(nodes), u8p), _p(node_off, u64p), n_nodes, _p(keys32, u8p), n_keys, _p(roots32, u8p),
+                                   roots32.size // 32, _p(status, u8p), _p(voff, u64p), _p(vlen, u32p), threads)
+        return status[:n_keys], voff[:n_keys], vlen[:n_keys]
+
     # -- synthetic --
     def synth_c2(self, n, depth=8, first=0, corrupt=True, seed=0x5048414E54, threads=8):
         per = self.lib.oracle_synth_c2_bytes_per_proof(depth)

@@ -232,3 +232,45 @@ def test_full_size_c3_property(ctx):
     assert (d_status.cpu().numpy() == expect).all()
     del d_nodes, d_off
     torch.cuda.empty_cache()
+
+
+def test_witness_as_unordered_node_set(ctx, oracle, golden):
+    """W: bag-of-nodes witnesses (execution-witness shape) -- GPU vs oracle, incl. missing nodes, junk nodes, fixture tries"""
+    from test_oracle_proofs import shuffled_bag
+    rng = np.random.default_rng(12)
+    w = oracle.synth_blocks(8, txs=60, first=30, threads=8)       # block 37 is corrupted
+    victim = int(w["node_index"][int(w["proof_first"][11]) + 3])
+    for drop, extra in ((None, 0), (None, 40), (victim, 10)):
+        nodes, node_off = shuffled_bag(w, rng, drop=drop, extra=extra)
+        want = oracle.verify_bag(nodes, node_off, w["keys32"], w["roots32"], threads=8)
+        n = w["n_proofs"]
+        bitmap = np.zeros((n + 63) // 64, np.uint64)
+        status = np.full(n, 77, np.uint8)
+        voff = np.zeros(n, np.uint64)
+        vlen = np.zeros(n, np.uint32)
+        ctx.set_flags(0)
+        ctx.verify_witness(len(node_off) - 1, nodes, node_off, n, w["keys32"], w["roots32"], n, bitmap, status, voff, vlen)
+        assert (status == want[0]).all(), np.nonzero(status != want[0])[0][:10]
+        ok = status == 1
+        assert (voff[ok] == want[1][ok]).all() and (vlen[ok] == want[2][ok]).all()
+        bits = np.unpackbits(bitmap.view(np.uint8), bitorder="little")[:n]
+        assert (bits == ((status == 1) | (status == 2))).all()
+        if drop is not None:
+            assert (status == 3).any()
+    # a real trie: fixture accounts, present + absent keys, one root for all
+    g = golden("fixture_states.json.gz")
+    accounts = max(g["tables"].values(), key=len)[:120]
+    items = secure_account_items(oracle.keccak256, oracle.mptize, accounts)
+    trie = oracle.trie(items)
+    bag = {}
+    keys = [k for k, _ in items] + [oracle.keccak256(bytes([i])) for i in range(20)]
+    for k in keys:
+        for nd in trie.prove(k):
+            bag[nd] = 1
+    nodes, node_off = oracle_lib.csr(list(bag), np.uint64)
+    keys32 = np.frombuffer(b"".join(keys), np.uint8)
+    root = np.frombuffer(trie.root(), np.uint8)
+    want = oracle.verify_bag(nodes, node_off, keys32, root)
+    status = np.zeros(len(keys), np.uint8)
+    ctx.verify_witness(len(node_off) - 1, nodes, node_off, len(keys), keys32, root, 1, None, status, None, None)
+    assert (status == want[0]).all() and (status[:len(items)] == 1).all() and (status[len(items):] == 2).all()

@@ -192,3 +192,37 @@ def test_ctrie_update_matches_full_rebuild(oracle):
     if len(set(pos)) == len(pos):
         assert t2.update(keys[perm].reshape(-1), [vals[i] for i in perm]) == r1
     assert t.update(keys.reshape(-1), vals) == r1
+
+
+def shuffled_bag(w, rng, drop=None, extra=0):
+    """the distinct nodes of a block witness as an unordered bag (optionally without node `drop`, plus junk nodes)"""
+    n = w["n_nodes"]
+    order = [int(i) for i in rng.permutation(n) if drop is None or int(i) != drop]
+    items = [w["nodes"][int(w["node_off"][i]):int(w["node_off"][i + 1])].tobytes() for i in order]
+    items += [rng.integers(0, 256, int(rng.integers(1, 600)), dtype=np.uint8).tobytes() for _ in range(extra)]
+    return oracle_lib.csr(items, np.uint64)
+
+
+def test_bag_witness_matches_chain_verdicts(oracle):
+    """the same proofs verified as chains and as an unordered set of nodes give the same present/absent verdicts"""
+    rng = np.random.default_rng(6)
+    w = oracle.synth_blocks(2, txs=40, first=0, threads=4)
+    chain = oracle.verify_proofs(w["nodes"], w["node_off"], w["proof_first"], w["keys32"], w["roots32"], threads=4, node_index=w["node_index"])
+    nodes, node_off = shuffled_bag(w, rng, extra=25)
+    st, voff, vlen = oracle.verify_bag(nodes, node_off, w["keys32"], w["roots32"], threads=4)
+    assert (st == chain[1]).all() and (st == 1).all()
+    vals_chain = [w["nodes"][int(o):int(o) + int(l)].tobytes() for o, l in zip(chain[2], chain[3])]
+    vals_bag = [nodes[int(o):int(o) + int(l)].tobytes() for o, l in zip(voff, vlen)]
+    assert vals_chain == vals_bag
+    # drop one node: every key whose path crosses it reports "missing" (3), the others are untouched
+    victim = int(w["node_index"][int(w["proof_first"][5]) + 2])
+    nodes2, node_off2 = shuffled_bag(w, rng, drop=victim)
+    st2, _, _ = oracle.verify_bag(nodes2, node_off2, w["keys32"], w["roots32"], threads=4)
+    uses = np.array([victim in w["node_index"][int(a):int(b)] for a, b in zip(w["proof_first"][:-1], w["proof_first"][1:])])
+    assert (st2[uses] == 3).all() and (st2[~uses] == 1).all() and uses.any()
+    # absent keys and the empty root
+    k = rng.integers(0, 256, 32, dtype=np.uint8)
+    st3, _, _ = oracle.verify_bag(nodes, node_off, k, w["roots32"][:32].copy())
+    assert st3[0] in (2, 3)  # a random key leaves the materialised paths: absent if it dies in a known node, missing otherwise
+    empty = np.frombuffer(bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"), np.uint8)
+    assert oracle.verify_bag(nodes, node_off, k, empty)[0][0] == 2
