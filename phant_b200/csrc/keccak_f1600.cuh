@@ -166,20 +166,22 @@ template <int UNROLL>
 __device__ __forceinline__ void absorb_final_smem(uint64_t (&st)[25], uint32_t sa, uint32_t rem)
 {
     const uint32_t a4 = sa & ~3u, sh = (sa & 3u) * 8;
+    // words [0, nfw) are whole message words, word nfw holds the last `tail` bytes and the 0x01 pad, the rest is zero:
+    // only the boundary word needs a mask, so everything else is a predicated load + funnel + xor
+    const uint32_t nfw = rem >> 2, tail = rem & 3u;
+    const uint32_t bmask = (1u << (8 * tail)) - 1u, pad = 1u << (8 * tail);
     uint32_t prev = rem ? lds32(a4) : 0;
 #pragma unroll
     for (int j = 0; j < 2 * KECCAK_RATE_WORDS; ++j) {
-        const int valid = (int)rem - 4 * j; // message bytes in 32-bit word j
-        uint32_t word = 0, next = 0;
-        if (valid > 0) {
-            next = lds32(a4 + 4 * (j + 1));
+        uint32_t word = 0;
+        if ((uint32_t)j < nfw || ((uint32_t)j == nfw && tail)) {
+            const uint32_t next = lds32(a4 + 4 * (j + 1));
             word = __funnelshift_r(prev, next, sh);
-            if (valid < 4) word &= (1u << (8 * valid)) - 1u;
+            prev = next;
         }
-        if (valid >= 0 && valid < 4) word ^= 1u << (8 * valid);
+        if ((uint32_t)j == nfw) word = (word & bmask) ^ pad;
         if (j == 2 * KECCAK_RATE_WORDS - 1) word ^= 0x80000000u;
         st[j >> 1] ^= (j & 1) ? ((uint64_t)word << 32) : (uint64_t)word;
-        prev = next;
     }
     keccak_f1600<UNROLL>(st);
 }
