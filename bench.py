@@ -92,11 +92,12 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
-    sample = 131072
+    sample = int(os.environ.get("PHANT_BENCH_CPU_SAMPLE", "131072"))
     steps = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_arm(sample, target_cpu_seconds=max(2.0, 20.0 / max(1, args.steps)), threads=threads)
+        base = cpu_arm(sample, target_cpu_seconds=max(2.0, float(os.environ.get("PHANT_BENCH_CPU_SECONDS", "20")) / max(1, args.steps)),
+                       threads=threads)
         if i >= args.warmup:
             steps.append(base["value"])
     value = statistics.mean(steps)

@@ -1,4 +1,4 @@
-/* keccak.c -- TEST INFRASTRUCTURE (see oracle.h).  Plain-C restatement of Keccak-256.
+/* keccak_port.c -- TEST INFRASTRUCTURE (see oracle.h).  Plain-C restatement of Keccak-256.
  *
  * Follows the sponge of ethash/lib/keccak/keccak.c:301-354 (rate 136 B, whole blocks absorbed as
  * little-endian 64-bit words, tail + 0x01 pad byte, 0x80 into the last rate byte, one final

@@ -55,6 +55,36 @@ def main():
         assert rc == 0 and ctx.mpt_root(keys, koff, vals, voff, n) == out.tobytes()
         print(json.dumps({"what": f"M secure trie {n} keys x 80 B", "gpu_ms": g * 1e3, "cpu_1thread_ms": c * 1e3, "launches_per_call": st["launches"] // 4,
                           "keys_per_s_gpu": n / g}), flush=True)
+    # ---- M batched: 3,000 tries of 100 withdrawals in one forest build vs one call each ----
+    lists = []
+    for t in range(3000):
+        wd = [rng.integers(0, 256, 48, dtype=np.uint8).tobytes() for _ in range(100)]
+        lists.append(index_trie_items(wd))
+    flat = [kv for l in lists for kv in l]
+    keys, koff = oracle_lib.csr([k for k, _ in flat], np.uint32)
+    vals, voff = oracle_lib.csr([v for _, v in flat], np.uint64)
+    seg = np.zeros(len(lists) + 1, np.uint32)
+    seg[1:] = np.cumsum([len(l) for l in lists])
+    g = timeit(lambda: ctx.mpt_roots(keys, koff, vals, voff, seg, len(lists)), 5)
+    t0 = time.perf_counter()
+    want = [o.mptize(l) for l in lists[:300]]
+    c = (time.perf_counter() - t0) * 10
+    assert ctx.mpt_roots(keys, koff, vals, voff, seg, len(lists))[:300] == want
+    print(json.dumps({"what": "M batched: 3000 index tries x 100 items, one phant_gpu_mpt_roots call", "gpu_ms": g * 1e3, "cpu_1thread_ms": c * 1e3,
+                      "tries_per_s_gpu": len(lists) / g}), flush=True)
+    # ---- S: state root of 500k accounts, 10% with 8 storage slots ----
+    na = 500_000
+    addr = rng.integers(0, 256, na * 20, dtype=np.uint8)
+    nonce = rng.integers(0, 1000, na).astype(np.uint64)
+    bal = np.zeros((na, 32), np.uint8); bal[:, 20:] = rng.integers(0, 256, (na, 12), dtype=np.uint8)
+    code = np.zeros(1, np.uint8); coff = np.zeros(na + 1, np.uint64)
+    has = rng.random(na) < 0.1
+    soff = np.zeros(na + 1, np.uint64); soff[1:] = np.cumsum(np.where(has, 8, 0))
+    ns = int(soff[-1])
+    skeys = rng.integers(0, 256, ns * 32, dtype=np.uint8); svals = rng.integers(1, 256, ns * 32, dtype=np.uint8)
+    g = timeit(lambda: ctx.state_root(na, addr, nonce, np.ascontiguousarray(bal.reshape(-1)), code, coff, skeys, svals, soff), 3)
+    print(json.dumps({"what": f"S state root: {na} accounts, {ns} storage slots (host pointers, pageable)", "gpu_ms": g * 1e3,
+                      "accounts_per_s": na / g}), flush=True)
     # ---- U: config C4 ----
     t = ctx.trie_open(6)
     n = 100_000
