@@ -165,6 +165,25 @@ class StateDB:
         return ctx.state_root(n, addr, nonce, bal, code, coff, skeys, svals, np.array(soff, np.uint64))
 
 
+def run_block_post_checks(ctx, header, encoded_txs, encoded_receipts, encoded_withdrawals, statedb=None):
+    """The root comparisons at the end of Blockchain.runBlock (src/blockchain/blockchain.zig:76-90), all tries of the block
+    in ONE forest build.  `header` is a dict with transactions_root / receipts_root / withdrawals_root (/ state_root).
+    Returns the list of mismatching field names (empty = block passes).  The state-root comparison is the one phant has
+    commented out (:83-85); it runs when a StateDB is given."""
+    lists = [encoded_txs, encoded_withdrawals] + ([encoded_receipts] if encoded_receipts is not None else [])
+    roots = calculate_mpt_roots(ctx, lists)
+    bad = []
+    if roots[0] != header["transactions_root"]:
+        bad.append("transactions_root")
+    if roots[1] != header["withdrawals_root"]:
+        bad.append("withdrawals_root")
+    if encoded_receipts is not None and roots[2] != header["receipts_root"]:
+        bad.append("receipts_root")
+    if statedb is not None and statedb.root(ctx) != header["state_root"]:
+        bad.append("state_root")
+    return bad
+
+
 class Log:
     """src/types/receipt.zig:65-69"""
 

@@ -145,3 +145,29 @@ def test_batched_list_roots(ctx, golden, oracle):
     two = mptize_many(ctx, [[KeyVal(b"\x02", b"x")], [KeyVal(b"\x01", b"y")], []])
     assert two[0] == oracle.mptize([(b"\x02", b"x")]) and two[1] == oracle.mptize([(b"\x01", b"y")])
     assert two[2].hex() == "56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"
+
+
+def test_run_block_post_checks(ctx, golden):
+    """H12: the post-execution root comparisons of runBlock on every valid fixture block (receipts are not in the
+    fixtures, so that root is skipped), with the last block's post state"""
+    from phant_b200.host import AccountState, StateDB, run_block_post_checks
+    g = golden("fixture_states.json.gz")
+    checked = 0
+    for t in g["tests"][:25]:
+        if not t["blocks"]:
+            continue
+        db = StateDB()
+        for a in g["tables"][t["post"]]:
+            db.db[bytes.fromhex(a["address"])] = AccountState(a["nonce"], int(a["balance"], 16), bytes.fromhex(a["code"]),
+                                                              {int(k, 16): int(v, 16) for k, v in a["storage"].items()})
+        for i, b in enumerate(t["blocks"]):
+            last = i == len(t["blocks"]) - 1
+            header = {"transactions_root": bytes.fromhex(b["transactionsTrie"]), "withdrawals_root": bytes.fromhex(b["withdrawalsRoot"]),
+                      "state_root": bytes.fromhex(t["post_root"])}
+            txs = [bytes.fromhex(x) for x in b["tx_values"]]
+            wds = [bytes.fromhex(x) for x in b["wd_values"]]
+            assert run_block_post_checks(ctx, header, txs, None, wds, db if last else None) == []
+            header["withdrawals_root"] = bytes(32)
+            assert run_block_post_checks(ctx, header, txs, None, wds) == ["withdrawals_root"]
+            checked += 1
+    assert checked >= 25
