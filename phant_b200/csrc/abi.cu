@@ -231,6 +231,22 @@ int phant_gpu_ctx::hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64
     return PHANT_GPU_OK;
 }
 
+int phant_gpu_ctx::hash_slots(const uint8_t* d_msgs, const uint64_t* d_off, const uint64_t* d_len, uint64_t n, uint8_t* d_out)
+{
+    phant_gpu_ctx* ctx = this;
+    if (n == 0) return PHANT_GPU_OK;
+    KeccakVariant variant = KECCAK_STAGED;
+    if (flags & PHANT_GPU_FLAG_KECCAK_DIRECT) variant = KECCAK_DIRECT;
+    if (flags & PHANT_GPU_FLAG_KECCAK_WARP) variant = KECCAK_WARP;
+    if (variant == KECCAK_STAGED && ((uintptr_t)d_msgs & 15)) variant = KECCAK_DIRECT;
+    time_begin(0);
+    CU(launch_keccak(stream, device, variant, d_msgs, d_off, nullptr, n, d_out, nullptr, d_len));
+    time_end();
+    stats.launches++;
+    stats.keccak_msgs += n;
+    return PHANT_GPU_OK;
+}
+
 // offsets must start the CSR at off[0] (any value) and be monotone; returns total bytes via *total
 static int check_offsets_host(const uint64_t* off, uint64_t n, uint64_t* total)
 {

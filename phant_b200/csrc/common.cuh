@@ -10,7 +10,8 @@ enum KeccakVariant { KECCAK_STAGED = 0, KECCAK_DIRECT = 1, KECCAK_WARP = 2 };
 // keccak_kernels.cu
 int keccak_num_sms(int device);
 cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, const uint8_t* msgs, const uint64_t* off,
-                          const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary /*nullable*/);
+                          const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary /*nullable*/,
+                          const uint64_t* len = nullptr /*nullable: message m = msgs[off[m] .. off[m] + len[m])*/);
 cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* off, uint64_t n, uint8_t* cls, uint32_t* idx,
                                    unsigned long long* perms);
 

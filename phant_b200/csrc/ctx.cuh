@@ -59,8 +59,11 @@ struct phant_gpu_ctx {
     int fail(cudaError_t e, const char* what, const char* file, int line);
     int hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64_t n, uint64_t total_bytes, uint8_t* d_out,
                  uint32_t* d_summary = nullptr);
+    // messages in slots: message m = d_msgs[d_off[m] .. d_off[m] + d_len[m]); no regrouping, no statistics pass
+    int hash_slots(const uint8_t* d_msgs, const uint64_t* d_off, const uint64_t* d_len, uint64_t n, uint8_t* d_out);
     // trie.cu
     int build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off, uint32_t n,
-                     const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots);
+                     const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots,
+                     uint32_t leaf_stride = 0 /* != 0: slot layout, see build_forest */);
     int sort_by_segment_and_hash(const uint8_t* d_hashes, const uint32_t* d_seg, uint32_t n, uint32_t* d_perm_out, DevBuf& scratch);
 };

@@ -76,11 +76,11 @@ template <int UNROLL>
 __global__ void __launch_bounds__(128)
 keccak256_direct_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
                         const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out,
-                        uint32_t* __restrict__ summary)
+                        uint32_t* __restrict__ summary, const uint64_t* __restrict__ len)
 {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t m = order ? order[i] : i;
-        const uint64_t beg = off[m], end = off[m + 1];
+        const uint64_t beg = off[m], end = len ? beg + len[m] : off[m + 1];
         uint64_t dg[4];
         keccak256_thread<UNROLL>(msgs + beg, end - beg, dg);
         if (summary) summary[m] = (end - beg) <= 4096 ? summarize_node(msgs + beg, (uint32_t)(end - beg)) : 0;
@@ -138,7 +138,7 @@ template <int UNROLL, int BLOCKS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
                         const uint32_t* __restrict__ order, uint64_t n, uint8_t* __restrict__ out,
-                        uint32_t* __restrict__ summary)
+                        uint32_t* __restrict__ summary, const uint64_t* __restrict__ len)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,7 +159,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
         if (active) {
             m = order ? order[idx] : idx;
             cur = off[m];
-            end = off[m + 1];
+            end = len ? cur + len[m] : off[m + 1]; // `len`: messages sit in fixed-stride slots (trie builders), not back to back
         }
         uint64_t st[25];
 #pragma unroll
@@ -219,7 +219,7 @@ __device__ __forceinline__ uint64_t rolv64(uint64_t x, uint32_t n) { return n ? 
 
 __global__ void __launch_bounds__(256)
 keccak256_warp_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off, uint64_t n,
-                      uint8_t* __restrict__ out)
+                      uint8_t* __restrict__ out, const uint64_t* __restrict__ lens)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp_id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -237,7 +237,7 @@ keccak256_warp_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restri
     const uint32_t FULL = 0xffffffffu;
 
     for (uint64_t m = warp_id; m < n; m += n_warps) {
-        const uint64_t beg = off[m], end = off[m + 1];
+        const uint64_t beg = off[m], end = lens ? beg + lens[m] : off[m + 1];
         uint64_t len = end - beg;
         const MsgView v = msg_view(msgs + beg);
         uint64_t s = 0; // my state lane (lanes >= 25 carry junk that nobody reads)
@@ -323,7 +323,7 @@ int keccak_num_sms(int device)
 
 template <int BLOCKS, int WARPS>
 static cudaError_t launch_staged(cudaStream_t s, int device, int sms, const uint8_t* msgs, const uint64_t* off, const uint32_t* order, uint64_t n,
-                                 uint8_t* out, uint32_t* summary)
+                                 uint8_t* out, uint32_t* summary, const uint64_t* len)
 {
     constexpr int SMEM = stage_smem(BLOCKS, WARPS);
     static int ctas_cache[64] = {0}; // function attributes are per device
@@ -339,12 +339,12 @@ static cudaError_t launch_staged(cudaStream_t s, int device, int sms, const uint
     uint64_t blocks = (tiles + WARPS - 1) / WARPS;
     const uint64_t cap = (uint64_t)sms * ctas_per_sm; // persistent: every CTA resident, striding over the tiles
     if (blocks > cap) blocks = cap;
-    keccak256_staged_kernel<2, BLOCKS, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, s>>>(msgs, off, order, n, out, summary);
+    keccak256_staged_kernel<2, BLOCKS, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, s>>>(msgs, off, order, n, out, summary, len);
     return cudaGetLastError();
 }
 
 cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, const uint8_t* msgs, const uint64_t* off,
-                          const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary)
+                          const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary, const uint64_t* len)
 {
     if (n == 0) return cudaSuccess;
     const int sms = keccak_num_sms(device);
@@ -361,31 +361,31 @@ cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, con
             }
         }
         switch (cfg) {
-        case 1: return launch_staged<3, 4>(s, device, sms, msgs, off, order, n, out, summary);
-        case 2: return launch_staged<2, 4>(s, device, sms, msgs, off, order, n, out, summary);
-        case 3: return launch_staged<1, 4>(s, device, sms, msgs, off, order, n, out, summary);
-        case 4: return launch_staged<4, 8>(s, device, sms, msgs, off, order, n, out, summary);
-        case 5: return launch_staged<2, 8>(s, device, sms, msgs, off, order, n, out, summary);
-        case 6: return launch_staged<4, 12>(s, device, sms, msgs, off, order, n, out, summary);
-        case 7: return launch_staged<4, 6>(s, device, sms, msgs, off, order, n, out, summary);
-        case 8: return launch_staged<3, 8>(s, device, sms, msgs, off, order, n, out, summary);
-        case 9: return launch_staged<4, 10>(s, device, sms, msgs, off, order, n, out, summary);
-        case 10: return launch_staged<4, 4>(s, device, sms, msgs, off, order, n, out, summary);
-        default: return launch_staged<4, 12>(s, device, sms, msgs, off, order, n, out, summary); // measured best: 1 CTA of 12 warps per SM
+        case 1: return launch_staged<3, 4>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 2: return launch_staged<2, 4>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 3: return launch_staged<1, 4>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 4: return launch_staged<4, 8>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 5: return launch_staged<2, 8>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 6: return launch_staged<4, 12>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 7: return launch_staged<4, 6>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 8: return launch_staged<3, 8>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 9: return launch_staged<4, 10>(s, device, sms, msgs, off, order, n, out, summary, len);
+        case 10: return launch_staged<4, 4>(s, device, sms, msgs, off, order, n, out, summary, len);
+        default: return launch_staged<4, 12>(s, device, sms, msgs, off, order, n, out, summary, len); // measured best: 1 CTA of 12 warps per SM
         }
     }
     case KECCAK_DIRECT: {
         uint64_t blocks = (n + 127) / 128;
         const uint64_t cap = (uint64_t)sms * 8;
         if (blocks > cap) blocks = cap;
-        keccak256_direct_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(msgs, off, order, n, out, summary);
+        keccak256_direct_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(msgs, off, order, n, out, summary, len);
         break;
     }
     case KECCAK_WARP: {
         uint64_t blocks = (n + 7) / 8;
         const uint64_t cap = (uint64_t)sms * 8;
         if (blocks > cap) blocks = cap;
-        keccak256_warp_kernel<<<(unsigned)blocks, 256, 0, s>>>(msgs, off, n, out);
+        keccak256_warp_kernel<<<(unsigned)blocks, 256, 0, s>>>(msgs, off, n, out, len);
         if (summary) cudaMemsetAsync(summary, 0, 4 * n, s); // this layout does not classify: the walk parses every node
         break;
     }

@@ -155,52 +155,79 @@ __global__ void init_roots_kernel(const uint32_t* __restrict__ seg_off, uint32_t
     }
 }
 
-// 16 threads per unit of the current level [beg, beg + cnt): find the branch depth, the branch value and the 16
-// child ranges; children with >= 2 keys become units of the next level.
+// One branch unit, 16 cooperating lanes (lane v looks after child nibble v): find the branch depth, the branch value and
+// the 16 child ranges; children with >= 2 keys become units of the next level (appended at next_base + counter).
+__device__ __forceinline__ void expand_unit(const Keys& k, const Tables& t, uint32_t id, uint32_t v, uint32_t sub, uint32_t next_base,
+                                            uint32_t* next_count, uint32_t* ext_count, uint32_t ext_base)
+{
+    const uint32_t lo = t.lo[id], hi = t.hi[id], from = t.ext_from[id];
+    uint32_t p = 0;
+    if (v == 0) {
+        p = lcp(k, lo, hi - 1);
+        const uint32_t l0 = nlen(k, lo);
+        if (l0 < p) p = l0;
+    }
+    p = __shfl_sync(sub, p, 0, 16);
+    const bool has_value = nlen(k, lo) == p;
+    const uint32_t first = lo + (has_value ? 1 : 0);
+    // lower bound of nibble value v at depth p within [first, hi)
+    uint32_t a = first, b = hi;
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (nib(k, mid, p) < v) a = mid + 1; else b = mid;
+    }
+    uint32_t ub = __shfl_down_sync(sub, a, 1, 16);
+    if (v == 15) ub = hi;
+    uint32_t child = 0;
+    const uint32_t c = ub - a;
+    if (c == 1) {
+        child = KIND_LEAF | a;
+        t.leaf_start[a] = p + 1;
+    } else if (c >= 2) {
+        const uint32_t nid = next_base + atomicAdd(next_count, 1u);
+        t.lo[nid] = a; t.hi[nid] = ub; t.ext_from[nid] = p + 1;
+        child = KIND_NODE | nid;
+    }
+    t.child[16 * id + v] = child;
+    if (v == 0) {
+        t.depth[id] = p;
+        t.has_value[id] = has_value ? 1 : 0;
+        if (has_value) t.leaf_start[lo] = NONE;
+        if (p > from) t.ext_list[ext_base + atomicAdd(ext_count, 1u)] = id;
+    }
+}
+
+// one BFS level per launch (large tries)
 __global__ void __launch_bounds__(128)
 expand_kernel(Keys k, Tables t, uint32_t beg, uint32_t cnt, uint32_t next_base, uint32_t* counters /*[1]=next units, [2]=ext in this level*/)
 {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t v = threadIdx.x & 15;
     const uint32_t sub = 0xffffu << (threadIdx.x & 16); // my half-warp
-    for (uint32_t u = gid >> 4; u < cnt; u += (gridDim.x * blockDim.x) >> 4) { // the 16 lanes of a half-warp share u
-        const uint32_t id = beg + u;
-        const uint32_t lo = t.lo[id], hi = t.hi[id], from = t.ext_from[id];
-        uint32_t p = 0;
-        if (v == 0) {
-            p = lcp(k, lo, hi - 1);
-            const uint32_t l0 = nlen(k, lo);
-            if (l0 < p) p = l0;
-        }
-        p = __shfl_sync(sub, p, 0, 16);
-        const bool has_value = nlen(k, lo) == p;
-        const uint32_t first = lo + (has_value ? 1 : 0);
-        // lower bound of nibble value v at depth p within [first, hi)
-        uint32_t a = first, b = hi;
-        while (a < b) {
-            const uint32_t mid = (a + b) >> 1;
-            if (nib(k, mid, p) < v) a = mid + 1; else b = mid;
-        }
-        uint32_t ub = __shfl_down_sync(sub, a, 1, 16);
-        if (v == 15) ub = hi;
-        uint32_t child = 0;
-        const uint32_t c = ub - a;
-        if (c == 1) {
-            child = KIND_LEAF | a;
-            t.leaf_start[a] = p + 1;
-        } else if (c >= 2) {
-            const uint32_t nid = next_base + atomicAdd(&counters[1], 1u);
-            t.lo[nid] = a; t.hi[nid] = ub; t.ext_from[nid] = p + 1;
-            child = KIND_NODE | nid;
-        }
-        t.child[16 * id + v] = child;
-        if (v == 0) {
-            t.depth[id] = p;
-            t.has_value[id] = has_value ? 1 : 0;
-            if (has_value) t.leaf_start[lo] = NONE;
-            if (p > from) t.ext_list[beg + atomicAdd(&counters[2], 1u)] = id;
-        }
+    for (uint32_t u = gid >> 4; u < cnt; u += (gridDim.x * blockDim.x) >> 4) // the 16 lanes of a half-warp share u
+        expand_unit(k, t, beg + u, threadIdx.x & 15, sub, next_base, &counters[1], &counters[2], beg);
+}
+
+// the whole BFS in ONE launch of one CTA (small tries are launch-bound): levels[0] = number of levels, then
+// (begin, count, extensions) per level; stops at max_levels (the caller sizes it from the key length)
+__global__ void __launch_bounds__(1024)
+bfs_small_kernel(Keys k, Tables t, uint32_t first_cnt, uint32_t max_levels, uint32_t* __restrict__ levels)
+{
+    __shared__ uint32_t s_next, s_ext;
+    const uint32_t sub = 0xffffu << (threadIdx.x & 16);
+    uint32_t beg = 0, cnt = first_cnt, nl = 0;
+    while (cnt && nl < max_levels) {
+        if (threadIdx.x == 0) { s_next = 0; s_ext = 0; }
+        __syncthreads();
+        for (uint32_t u = threadIdx.x >> 4; u < cnt; u += blockDim.x >> 4)
+            expand_unit(k, t, beg + u, threadIdx.x & 15, sub, beg + cnt, &s_next, &s_ext, beg);
+        __syncthreads();
+        if (threadIdx.x == 0) { levels[1 + 3 * nl] = beg; levels[2 + 3 * nl] = cnt; levels[3 + 3 * nl] = s_ext; }
+        beg += cnt;
+        cnt = s_next;
+        ++nl;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) { levels[0] = nl; levels[1 + 3 * max_levels] = cnt; } // cnt != 0: deeper than max_levels (never with max_levels >= key nibbles)
 }
 
 // ---------------------------------------------------------------- leaves
@@ -254,12 +281,13 @@ leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __re
 }
 // reference of item j (leaf or encoded unit): raw RLP when < 32 bytes, else 0xa0 || digest
 __global__ void finalize_ref_kernel(uint32_t cnt, const uint32_t* __restrict__ ids /*nullable: identity*/, uint32_t id_base,
-                                    const uint64_t* __restrict__ aoff, const uint8_t* __restrict__ arena,
+                                    const uint64_t* __restrict__ aoff, const uint64_t* __restrict__ alen /*nullable: CSR*/,
+                                    const uint8_t* __restrict__ arena,
                                     const uint8_t* __restrict__ digests, uint32_t ref_base, Tables t, uint8_t* __restrict__ top_digest)
 {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
         const uint32_t id = ids ? ids[j] : id_base + j;
-        const uint64_t len = aoff[j + 1] - aoff[j];
+        const uint64_t len = alen ? alen[j] : aoff[j + 1] - aoff[j];
         uint8_t* r = t.ref + 33ull * (ref_base + id);
         if (len == 0) { t.ref_len[ref_base + id] = 0; continue; } // not a leaf (branch-value key)
         if (len < 32) {
@@ -300,13 +328,13 @@ __global__ void branch_size_kernel(Keys k, Vals vals, Tables t, uint32_t n_keys,
 // one warp per unit: lane v < 16 places child v at the prefix sum of the reference sizes, all lanes copy the value
 __global__ void __launch_bounds__(256)
 branch_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n_keys, uint32_t beg, uint32_t cnt, const uint64_t* __restrict__ aoff,
-                     uint8_t* __restrict__ arena)
+                     const uint64_t* __restrict__ alen /*nullable: CSR*/, uint8_t* __restrict__ arena)
 {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < cnt; u += (gridDim.x * blockDim.x) >> 5) {
         const uint32_t id = beg + u;
         uint8_t* out = arena + aoff[u];
-        const uint64_t total = aoff[u + 1] - aoff[u];
+        const uint64_t total = alen ? alen[u] : aoff[u + 1] - aoff[u];
         uint32_t c = 0, sz = 0, ri = 0;
         if (lane < 16) {
             c = t.child[16 * id + lane];
@@ -383,6 +411,11 @@ __global__ void gather_roots_kernel(Tables t, uint32_t n_seg, const uint8_t* __r
     }
 }
 
+__global__ void fixed_offsets_kernel(uint64_t* off, uint64_t n, uint64_t stride)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) off[i] = stride * i;
+}
+
 unsigned grid1d(int device, uint64_t work_items, unsigned block, unsigned per_item = 1)
 {
     uint64_t blocks = (work_items * per_item + block - 1) / block;
@@ -408,7 +441,8 @@ int scan_sizes(phant_gpu_ctx* ctx, uint64_t* sizes, uint64_t* offs, uint64_t cnt
 // forest builder: keys/vals on the device, keys sorted inside each segment; roots = n_seg * 32 bytes (device)
 // ------------------------------------------------------------------------------------------------
 int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off,
-                                uint32_t n, const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots)
+                                uint32_t n, const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots,
+                                uint32_t leaf_stride)
 {
     phant_gpu_ctx* ctx = this;
     cudaStream_t s = stream;
@@ -449,9 +483,22 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
     CU(cudaStreamSynchronize(s));
     if (h[4]) return PHANT_GPU_E_INVALID;
 
-    // ---- top-down: one launch per BFS level ----
+    // ---- top-down: one launch per BFS level, or the whole BFS in one single-CTA launch for small tries ----
     std::vector<uint32_t> level_beg, level_cnt, level_ext;
     uint32_t beg = 0, cnt = h[0];
+    if (cnt && leaf_stride && n <= 8192) { // slot layout implies keys <= 64 bytes = 128 nibbles: at most 129 levels
+        constexpr uint32_t MAXL = 160;
+        RC(d_tmp_b.reserve(ctx, 4 * (2 + 3 * MAXL)));
+        uint32_t* d_levels = (uint32_t*)d_tmp_b.ptr;
+        bfs_small_kernel<<<1, 1024, 0, s>>>(k, t, cnt, MAXL, d_levels);
+        stats.launches++;
+        std::vector<uint32_t> hl(2 + 3 * MAXL);
+        CU(cudaMemcpyAsync(hl.data(), d_levels, 4 * hl.size(), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (hl[1 + 3 * MAXL] != 0) return PHANT_GPU_E_INVALID;
+        for (uint32_t l = 0; l < hl[0]; ++l) { level_beg.push_back(hl[1 + 3 * l]); level_cnt.push_back(hl[2 + 3 * l]); level_ext.push_back(hl[3 + 3 * l]); }
+        cnt = 0;
+    }
     while (cnt) {
         CU(cudaMemsetAsync(counters + 1, 0, 8, s));
         expand_kernel<<<grid1d(device, cnt, 128, 16), 128, 0, s>>>(k, t, beg, cnt, beg + cnt, counters);
@@ -464,6 +511,26 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         if ((uint64_t)beg + cnt > cap) return PHANT_GPU_E_CUDA; // cannot happen: a trie over n keys has < n branch units
     }
 
+    // Two arena layouts.  General: exact sizes, exclusive scan, one read-back of the total per pass.  Slots (leaf_stride != 0:
+    // the caller vouches that no key is a prefix of another -- so no branch carries a value -- and bounds the leaf size):
+    // every node gets a fixed-stride slot, the Keccak kernel takes (offset, length) pairs, and no pass needs a scan or
+    // a host round trip.  Small tries are launch-bound, so this halves their latency.
+    const bool slots = leaf_stride != 0;
+    constexpr uint32_t BRANCH_STRIDE = 544, EXT_STRIDE = 128;
+    uint64_t* fixed_leaf = nullptr; uint64_t* fixed_branch = nullptr; uint64_t* fixed_ext = nullptr;
+    if (slots) {
+        uint32_t max_level = 1;
+        for (uint32_t c : level_cnt) if (c > max_level) max_level = c;
+        RC(d_scan_a.reserve(ctx, 8ull * (n + 2) + 8ull * (max_level + 2) * 2));
+        fixed_leaf = (uint64_t*)d_scan_a.ptr;
+        fixed_branch = fixed_leaf + (n + 2);
+        fixed_ext = fixed_branch + (max_level + 2);
+        fixed_offsets_kernel<<<grid1d(device, n + 1, 256), 256, 0, s>>>(fixed_leaf, n, leaf_stride);
+        fixed_offsets_kernel<<<grid1d(device, max_level + 1, 256), 256, 0, s>>>(fixed_branch, max_level, BRANCH_STRIDE);
+        fixed_offsets_kernel<<<grid1d(device, max_level + 1, 256), 256, 0, s>>>(fixed_ext, max_level, EXT_STRIDE);
+        stats.launches += 3;
+    }
+
     // ---- leaves: sizes -> offsets -> encode -> hash -> references ----
     uint8_t* leaf_digests = nullptr;
     if (n) {
@@ -471,17 +538,22 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         uint64_t* sizes = (uint64_t*)d_b4.ptr;
         uint64_t* offs = sizes + (n + 1);
         leaf_size_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, vals, t, n, sizes);
-        RC(scan_sizes(ctx, sizes, offs, n));
-        uint64_t total = 0;
-        CU(cudaMemcpyAsync(&total, offs + n, 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        uint64_t total = (uint64_t)n * leaf_stride;
+        if (slots) offs = fixed_leaf;
+        else {
+            RC(scan_sizes(ctx, sizes, offs, n));
+            CU(cudaMemcpyAsync(&total, offs + n, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+        }
         RC(d_b5.reserve(ctx, total + 64));
         RC(d_b6.reserve(ctx, 32ull * n));
         leaf_digests = (uint8_t*)d_b6.ptr;
         leaf_encode_kernel<<<grid1d(device, n, 256, 32), 256, 0, s>>>(k, vals, t, n, offs, (uint8_t*)d_b5.ptr);
         stats.launches += 2;
-        RC(hash_csr((const uint8_t*)d_b5.ptr, offs, n, total, leaf_digests));
-        finalize_ref_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(n, nullptr, 0, offs, (const uint8_t*)d_b5.ptr, leaf_digests, 0, t, nullptr);
+        if (slots) RC(hash_slots((const uint8_t*)d_b5.ptr, offs, sizes, n, leaf_digests));
+        else RC(hash_csr((const uint8_t*)d_b5.ptr, offs, n, total, leaf_digests));
+        finalize_ref_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(n, nullptr, 0, offs, slots ? sizes : nullptr, (const uint8_t*)d_b5.ptr, leaf_digests, 0, t,
+                                                                 nullptr);
         stats.launches++;
     }
 
@@ -492,30 +564,40 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         uint64_t* sizes = (uint64_t*)d_b7.ptr;
         uint64_t* offs = sizes + (lc + 1);
         branch_size_kernel<<<grid1d(device, lc, 128), 128, 0, s>>>(k, vals, t, n, lb, lc, sizes);
-        RC(scan_sizes(ctx, sizes, offs, lc));
-        uint64_t total = 0;
-        CU(cudaMemcpyAsync(&total, offs + lc, 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        uint64_t total = (uint64_t)lc * BRANCH_STRIDE;
+        if (slots) offs = fixed_branch;
+        else {
+            RC(scan_sizes(ctx, sizes, offs, lc));
+            CU(cudaMemcpyAsync(&total, offs + lc, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+        }
         RC(d_b8.reserve(ctx, total + 64));
         RC(d_b9.reserve(ctx, 32ull * lc));
-        branch_encode_kernel<<<grid1d(device, lc, 256, 32), 256, 0, s>>>(k, vals, t, n, lb, lc, offs, (uint8_t*)d_b8.ptr);
+        branch_encode_kernel<<<grid1d(device, lc, 256, 32), 256, 0, s>>>(k, vals, t, n, lb, lc, offs, slots ? sizes : nullptr, (uint8_t*)d_b8.ptr);
         stats.launches += 2;
-        RC(hash_csr((const uint8_t*)d_b8.ptr, offs, lc, total, (uint8_t*)d_b9.ptr));
-        finalize_ref_kernel<<<grid1d(device, lc, 256), 256, 0, s>>>(lc, nullptr, lb, offs, (const uint8_t*)d_b8.ptr, (const uint8_t*)d_b9.ptr, n, t,
-                                                                  t.top_digest);
+        if (slots) RC(hash_slots((const uint8_t*)d_b8.ptr, offs, sizes, lc, (uint8_t*)d_b9.ptr));
+        else RC(hash_csr((const uint8_t*)d_b8.ptr, offs, lc, total, (uint8_t*)d_b9.ptr));
+        finalize_ref_kernel<<<grid1d(device, lc, 256), 256, 0, s>>>(lc, nullptr, lb, offs, slots ? sizes : nullptr, (const uint8_t*)d_b8.ptr,
+                                                                  (const uint8_t*)d_b9.ptr, n, t, t.top_digest);
         stats.launches++;
         if (le) {
             const uint32_t* ids = t.ext_list + lb;
             ext_size_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, sizes);
-            RC(scan_sizes(ctx, sizes, offs, le));
-            CU(cudaMemcpyAsync(&total, offs + le, 8, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
+            total = (uint64_t)le * EXT_STRIDE;
+            offs = sizes + (lc + 1);
+            if (slots) offs = fixed_ext;
+            else {
+                RC(scan_sizes(ctx, sizes, offs, le));
+                CU(cudaMemcpyAsync(&total, offs + le, 8, cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+            }
             RC(d_b8.reserve(ctx, total + 64));
             ext_encode_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, offs, (uint8_t*)d_b8.ptr);
             stats.launches += 2;
-            RC(hash_csr((const uint8_t*)d_b8.ptr, offs, le, total, (uint8_t*)d_b9.ptr));
-            finalize_ref_kernel<<<grid1d(device, le, 256), 256, 0, s>>>(le, ids, 0, offs, (const uint8_t*)d_b8.ptr, (const uint8_t*)d_b9.ptr, n, t,
-                                                                      t.top_digest);
+            if (slots) RC(hash_slots((const uint8_t*)d_b8.ptr, offs, sizes, le, (uint8_t*)d_b9.ptr));
+            else RC(hash_csr((const uint8_t*)d_b8.ptr, offs, le, total, (uint8_t*)d_b9.ptr));
+            finalize_ref_kernel<<<grid1d(device, le, 256), 256, 0, s>>>(le, ids, 0, offs, slots ? sizes : nullptr, (const uint8_t*)d_b8.ptr,
+                                                                      (const uint8_t*)d_b9.ptr, n, t, t.top_digest);
             stats.launches++;
         }
     }
@@ -523,6 +605,31 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
     stats.launches++;
     CU(cudaGetLastError());
     return PHANT_GPU_OK;
+}
+
+// Slot layout is possible when no key of a trie is a prefix of its successor (then no branch carries a value) and the
+// leaves are small: returns the leaf slot stride, or 0 for the general layout.  Keys are sorted, so a prefix relation
+// always shows up between neighbours.
+static uint32_t leaf_stride_for(const uint8_t* keys, const uint32_t* key_off, const uint64_t* val_off, uint64_t lo, uint64_t hi,
+                                uint32_t* max_k, uint64_t* max_v)
+{
+    for (uint64_t i = lo; i < hi; ++i) {
+        const uint32_t kl = key_off[i + 1] - key_off[i];
+        const uint64_t vl = val_off[i + 1] - val_off[i];
+        if (kl > *max_k) *max_k = kl;
+        if (vl > *max_v) *max_v = vl;
+        if (i + 1 < hi) {
+            const uint32_t kn = key_off[i + 2] - key_off[i + 1];
+            if (kl <= kn && memcmp(keys + key_off[i], keys + key_off[i + 1], kl) == 0) return 0; // prefix (or duplicate)
+        }
+    }
+    return 1;
+}
+static uint32_t stride_from(uint32_t max_k, uint64_t max_v, uint64_t n)
+{
+    if (max_k > 64 || max_v > 3072) return 0;
+    const uint32_t stride = (uint32_t)((max_v + max_k + 16 + 15) & ~15ull);
+    return (uint64_t)stride * n <= (1ull << 31) ? stride : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -539,11 +646,15 @@ extern "C" int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const
     if (n == 0) { memcpy(out_root, EMPTY, 32); return PHANT_GPU_OK; }
     cudaStream_t s = ctx->stream;
     const uint8_t* d_keys = keys; const uint32_t* d_koff = key_off; const uint8_t* d_vals = vals; const uint64_t* d_voff = val_off;
+    uint32_t leaf_stride = 0;
     if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS)) {
         for (uint64_t i = 0; i < n; ++i)
             if (key_off[i + 1] < key_off[i] || val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
         const uint64_t kb = key_off[n], vb = val_off[n];
         if ((kb && !keys) || (vb && !vals)) return PHANT_GPU_E_INVALID;
+        uint32_t max_k = 0;
+        uint64_t max_v = 0;
+        if (leaf_stride_for(keys, key_off, val_off, 0, n, &max_k, &max_v)) leaf_stride = stride_from(max_k, max_v, n);
         RC(ctx->d_msgs.reserve(ctx, kb + vb + 128));
         RC(ctx->d_off.reserve(ctx, 4 * (n + 1) + 8 * (n + 1) + 16));
         uint8_t* dk = (uint8_t*)ctx->d_msgs.ptr;
@@ -561,7 +672,8 @@ extern "C" int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const
     uint32_t seg[2] = {0, (uint32_t)n};
     CU(cudaMemcpyAsync(ctx->d_first.ptr, seg, 8, cudaMemcpyHostToDevice, s));
     RC(ctx->d_roots.reserve(ctx, 32));
-    RC(ctx->build_forest(d_keys, d_koff, d_vals, d_voff, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr));
+    RC(ctx->build_forest(d_keys, d_koff, d_vals, d_voff, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr,
+                         leaf_stride));
     CU(cudaMemcpyAsync(out_root, ctx->d_roots.ptr, 32, cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += 32;
     CU(cudaStreamSynchronize(s));
@@ -583,6 +695,11 @@ extern "C" int phant_gpu_mpt_roots(phant_gpu_ctx* ctx, const uint8_t* keys, cons
         if (key_off[i + 1] < key_off[i] || val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
     const uint64_t kb = n ? key_off[n] : 0, vb = n ? val_off[n] : 0;
     if ((kb && !keys) || (vb && !vals)) return PHANT_GPU_E_INVALID;
+    uint32_t leaf_stride = 0, max_k = 0;
+    uint64_t max_v = 0;
+    bool slot_ok = n > 0;
+    for (uint64_t t = 0; slot_ok && t < n_tries; ++t) slot_ok = leaf_stride_for(keys, key_off, val_off, seg_off[t], seg_off[t + 1], &max_k, &max_v) != 0;
+    if (slot_ok) leaf_stride = stride_from(max_k, max_v, n);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     // segment id of every key (the sortedness check must not compare across tries)
@@ -609,7 +726,7 @@ extern "C" int phant_gpu_mpt_roots(phant_gpu_ctx* ctx, const uint8_t* keys, cons
     if (n) CU(cudaMemcpyAsync(dsok, seg_of_key.data(), 4 * n, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s)); // seg_of_key is a local vector: the copy must finish before it goes out of scope
     ctx->stats.h2d_bytes += kb + vb + 16 * (n + 1) + 4 * (n_tries + 1);
-    RC(ctx->build_forest(dk, dko, dv, dvo, (uint32_t)n, dseg, (uint32_t)n_tries, dsok, (uint8_t*)ctx->d_roots.ptr));
+    RC(ctx->build_forest(dk, dko, dv, dvo, (uint32_t)n, dseg, (uint32_t)n_tries, dsok, (uint8_t*)ctx->d_roots.ptr, leaf_stride));
     CU(cudaMemcpyAsync(out_roots, ctx->d_roots.ptr, 32 * n_tries, cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += 32 * n_tries;
     CU(cudaStreamSynchronize(s));
@@ -751,10 +868,6 @@ __global__ void gather_rows32_kernel(const uint8_t* __restrict__ src, const uint
         q[0] = p[0];
         q[1] = p[1];
     }
-}
-__global__ void fixed_offsets_kernel(uint64_t* off, uint64_t n, uint64_t stride)
-{
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) off[i] = stride * i;
 }
 
 } // namespace
@@ -903,7 +1016,7 @@ extern "C" int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts
         CU(cub::DeviceScan::ExclusiveSum(nullptr, temp, (const uint32_t*)seg_cnt, seg_off, (int64_t)(n + 1), s));
         RC(ctx->d_cub.reserve(ctx, temp));
         CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.ptr, temp, (const uint32_t*)seg_cnt, seg_off, (int64_t)(n + 1), s));
-        RC(ctx->build_forest(fk, fko, fv, fvo, m, seg_off, (uint32_t)n, acc_sorted, sroots));
+        RC(ctx->build_forest(fk, fko, fv, fvo, m, seg_off, (uint32_t)n, acc_sorted, sroots, /*32-byte keys, values <= 33 B*/ 96));
     } else {
         CU(cudaMemsetAsync(seg_off, 0, 4ull * (n + 2), s));
         RC(ctx->build_forest(nullptr, seg_off, nullptr, nullptr, 0, seg_off, (uint32_t)n, nullptr, sroots)); // every storage trie empty
@@ -928,7 +1041,8 @@ extern "C" int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts
     RC(ctx->d_first.reserve(ctx, 64));
     CU(cudaMemcpyAsync(ctx->d_first.ptr, seg, 8, cudaMemcpyHostToDevice, s));
     RC(ctx->d_roots.reserve(ctx, 32));
-    RC(ctx->build_forest(ak, ako, av, avo, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr));
+    RC(ctx->build_forest(ak, ako, av, avo, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr,
+                         /*32-byte keys, account RLP <= 110 B*/ 160));
     CU(cudaMemcpyAsync(out_root, ctx->d_roots.ptr, 32, cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += 32;
     CU(cudaStreamSynchronize(s));
