@@ -211,6 +211,49 @@ def calculate_logs_blooms(ctx, receipts_logs):
     return [b.tobytes() for b in blooms[:n]], block.tobytes()
 
 
+def _rlp_str(b):
+    b = bytes(b)
+    if len(b) == 1 and b[0] < 0x80:
+        return b
+    if len(b) <= 55:
+        return bytes([0x80 + len(b)]) + b
+    ll = (len(b).bit_length() + 7) // 8
+    return bytes([0xb7 + ll]) + len(b).to_bytes(ll, "big") + b
+
+
+def _rlp_list(items):
+    body = b"".join(items)
+    if len(body) <= 55:
+        return bytes([0xc0 + len(body)]) + body
+    ll = (len(body).bit_length() + 7) // 8
+    return bytes([0xf7 + ll]) + len(body).to_bytes(ll, "big") + body
+
+
+class Receipt:
+    """src/types/receipt.zig:13-35: succeeded, cumulative_gas_used, bloom, logs.  `tx_type` (0 legacy) adds the EIP-2718
+    type byte in front of the RLP, which phant's struct does not carry yet (its receipts root only matches legacy blocks)."""
+
+    def __init__(self, succeeded, cumulative_gas_used, logs, tx_type=0):
+        self.succeeded, self.cumulative_gas_used, self.logs, self.tx_type = bool(succeeded), int(cumulative_gas_used), list(logs), tx_type
+        self.bloom = bytes(256)
+
+    def encode(self):
+        """Receipt.encode (receipt.zig:29-35): rlp([succeeded, cumulative_gas_used, bloom, logs])"""
+        gas = self.cumulative_gas_used.to_bytes(8, "big").lstrip(b"\x00")
+        logs = _rlp_list([_rlp_list([_rlp_str(l.address), _rlp_list([_rlp_str(t) for t in l.topics]), _rlp_str(l.data)]) for l in self.logs])
+        body = _rlp_list([_rlp_str(b"\x01" if self.succeeded else b""), _rlp_str(gas), _rlp_str(self.bloom), logs])
+        return (bytes([self.tx_type]) if self.tx_type else b"") + body
+
+
+def receipts_root(ctx, receipts):
+    """blockchain.zig:184-203: blooms of all receipts in one batched call (GPU), encodings on the host, receipts trie on
+    the GPU.  Returns (receipts_root, block logs bloom)."""
+    blooms, block_bloom = calculate_logs_blooms(ctx, [r.logs for r in receipts])
+    for r, b in zip(receipts, blooms):
+        r.bloom = b
+    return calculate_mpt_root(ctx, [r.encode() for r in receipts]), block_bloom
+
+
 def verify_witness_nodes(ctx, state_root, nodes, hashed_keys):
     """execution_payload.zig:177-178 for a witness that is an unordered SET of trie nodes (`state: [node, ...]`):
     -> status per key: 0 reject, 1 present, 2 absent, 3 node missing from the set"""

@@ -140,7 +140,15 @@ def evmone_kat():
     for _, topics in logs:
         for t in topics:
             assert t in hsrc
-    dump("logs_bloom_kat.json", {"source": "evmone/test/unittests/state_mpt_hash_test.cpp:118-190", "logs": logs, "bloom": bloom})
+    # the same receipt plus a log-free EIP-1559 receipt and the root of the two-receipt trie (state_mpt_hash_test.cpp:192-245)
+    receipts = [{"type": 0, "succeeded": True, "gas_used": 0x24522,
+                 "logs": [{"address": a, "topics": t, "data": d} for (a, t), d in
+                          zip(logs, ["0000000000000000000000000000000000000000000000000000000063ee2f6c", "", ""])]},
+                {"type": 2, "succeeded": True, "gas_used": 0x2cd9b, "logs": []}]
+    receipts_root = "7199a3a86010634dc205a1cdd6ec609f70b954167583cb3acb6a2e3057916016"
+    assert receipts_root in hsrc and "0x24522" in hsrc and "0x2cd9b" in hsrc and "63ee2f6c" in hsrc
+    dump("logs_bloom_kat.json", {"source": "evmone/test/unittests/state_mpt_hash_test.cpp:118-245", "logs": logs, "bloom": bloom,
+                                 "receipts": receipts, "receipts_root": receipts_root})
     dump("evmone_mpt_kat.json", {"source": "evmone/test/unittests/state_mpt_test.cpp:20-333, state_mpt_hash_test.cpp:19-66",
                                  "topologies": groups, "examples": examples, "states": states})
 

@@ -171,3 +171,16 @@ def test_run_block_post_checks(ctx, golden):
             assert run_block_post_checks(ctx, header, txs, None, wds) == ["withdrawals_root"]
             checked += 1
     assert checked >= 20
+
+
+def test_receipts_root_reference_vector(ctx, golden):
+    """N3 end to end: logs -> blooms (GPU) -> receipt encodings (host RLP) -> receipts trie (GPU), against the root quoted in
+    evmone/test/unittests/state_mpt_hash_test.cpp:192-245 (one legacy receipt with three logs, one log-free EIP-1559 receipt)"""
+    from phant_b200.host import Log, Receipt, receipts_root
+    g = golden("logs_bloom_kat.json")
+    receipts = [Receipt(r["succeeded"], r["gas_used"],
+                        [Log(bytes.fromhex(l["address"]), [bytes.fromhex(x) for x in l["topics"]], bytes.fromhex(l["data"])) for l in r["logs"]],
+                        tx_type=r["type"]) for r in g["receipts"]]
+    root, block_bloom = receipts_root(ctx, receipts)
+    assert root.hex() == g["receipts_root"]
+    assert receipts[0].bloom.hex() == g["bloom"] and block_bloom.hex() == g["bloom"]

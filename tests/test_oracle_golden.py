@@ -140,3 +140,17 @@ def test_tx_hash_reference_vectors(oracle, golden):
     """src/types/transaction.zig:275-314: three mainnet transactions (legacy, EIP-2930, EIP-1559)."""
     for c in golden("tx_hash_kat.json")["cases"]:
         assert oracle.keccak256(bytes.fromhex(c["encoded"])).hex() == c["hash"]
+
+
+def test_receipts_root_reference_vector(oracle, golden):
+    """evmone/test/unittests/state_mpt_hash_test.cpp:192-245: blooms + receipt encodings + index trie, all on the CPU side"""
+    from phant_b200.host import Log, Receipt
+    g = golden("logs_bloom_kat.json")
+    receipts = []
+    for r in g["receipts"]:
+        logs = [Log(bytes.fromhex(l["address"]), [bytes.fromhex(x) for x in l["topics"]], bytes.fromhex(l["data"])) for l in r["logs"]]
+        rc = Receipt(r["succeeded"], r["gas_used"], logs, tx_type=r["type"])
+        items = [x for l in logs for x in [l.address] + l.topics]
+        rc.bloom = oracle.logs_bloom(items, [0] * len(items), 1)[0].tobytes() if items else bytes(256)
+        receipts.append(rc)
+    assert oracle.mptize(index_trie_items([r.encode() for r in receipts])).hex() == g["receipts_root"]
