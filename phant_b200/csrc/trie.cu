@@ -127,19 +127,33 @@ struct Tables {
 };
 
 // ---------------------------------------------------------------- validation
-__global__ void check_sorted_kernel(Keys k, const uint32_t* __restrict__ seg_of_key, uint32_t n, uint32_t* bad)
+__global__ void check_sorted_kernel(Keys k, const uint64_t* __restrict__ val_off, const uint32_t* __restrict__ seg_of_key, uint32_t n,
+                                    uint32_t* flags /*[0] unsorted, [1] some key is a prefix of its successor, [2] max key bytes, [3] max value bytes*/)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.x * blockDim.x) {
-        if (seg_of_key && seg_of_key[i] != seg_of_key[i + 1]) continue;
-        const uint32_t la = k.off[i + 1] - k.off[i], lb = k.off[i + 2] - k.off[i + 1];
+    uint32_t max_k = 0, max_v = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t la = k.off[i + 1] - k.off[i];
+        const uint64_t lv = val_off[i + 1] - val_off[i];
+        max_k = la > max_k ? la : max_k;
+        const uint32_t lv32 = lv > 0xffffffffull ? 0xffffffffu : (uint32_t)lv;
+        max_v = lv32 > max_v ? lv32 : max_v;
+        if (i + 1 >= n || (seg_of_key && seg_of_key[i] != seg_of_key[i + 1])) continue;
+        const uint32_t lb = k.off[i + 2] - k.off[i + 1];
         const uint8_t* a = k.bytes + k.off[i];
         const uint8_t* b = k.bytes + k.off[i + 1];
         const uint32_t m = la < lb ? la : lb;
         uint32_t t = 0;
         while (t < m && a[t] == b[t]) ++t;
         const bool ok = t < m ? a[t] < b[t] : la < lb; // strictly increasing; a strict prefix sorts first
-        if (!ok) atomicExch(bad, 1u);
+        if (!ok) atomicExch(&flags[0], 1u);
+        if (t == la) atomicExch(&flags[1], 1u);        // key i is a prefix of key i+1: that branch will carry a value
     }
+    for (int o = 16; o; o >>= 1) {
+        const uint32_t ok = __shfl_down_sync(0xffffffffu, max_k, o), ov = __shfl_down_sync(0xffffffffu, max_v, o);
+        max_k = ok > max_k ? ok : max_k;
+        max_v = ov > max_v ? ov : max_v;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&flags[2], max_k); atomicMax(&flags[3], max_v); }
 }
 
 // ---------------------------------------------------------------- top-down
@@ -442,7 +456,7 @@ int scan_sizes(phant_gpu_ctx* ctx, uint64_t* sizes, uint64_t* offs, uint64_t cnt
 // ------------------------------------------------------------------------------------------------
 int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off,
                                 uint32_t n, const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots,
-                                uint32_t leaf_stride)
+                                int slots_hint)
 {
     phant_gpu_ctx* ctx = this;
     cudaStream_t s = stream;
@@ -472,8 +486,8 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
     CU(cudaMemsetAsync(t.leaf_start, 0xff, 4ull * cap, s));
 
     // keys must be strictly sorted inside each segment (mpt.zig:39 asserts)
-    if (n > 1) {
-        check_sorted_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, d_seg_of_key, n, counters + 4);
+    if (n) {
+        check_sorted_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, d_val_off, d_seg_of_key, n, counters + 4);
         stats.launches++;
     }
     init_roots_kernel<<<grid1d(device, n_seg, 256), 256, 0, s>>>(d_seg_off, n_seg, t, counters);
@@ -482,6 +496,13 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
     CU(cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (h[4]) return PHANT_GPU_E_INVALID;
+    // layout choice (see "Two arena layouts" below), from what the check kernel saw: slots need no branch values and small leaves
+    uint32_t leaf_stride = 0;
+    if (slots_hint > 0) leaf_stride = (uint32_t)slots_hint;
+    else if (slots_hint < 0 && n && !h[5] && h[6] <= 64 && h[7] <= 3072) {
+        const uint32_t st = (h[7] + h[6] + 16 + 15) & ~15u;
+        if ((uint64_t)st * n <= (1ull << 31)) leaf_stride = st;
+    }
 
     // ---- top-down: one launch per BFS level, or the whole BFS in one single-CTA launch for small tries ----
     std::vector<uint32_t> level_beg, level_cnt, level_ext;
@@ -607,31 +628,6 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
     return PHANT_GPU_OK;
 }
 
-// Slot layout is possible when no key of a trie is a prefix of its successor (then no branch carries a value) and the
-// leaves are small: returns the leaf slot stride, or 0 for the general layout.  Keys are sorted, so a prefix relation
-// always shows up between neighbours.
-static uint32_t leaf_stride_for(const uint8_t* keys, const uint32_t* key_off, const uint64_t* val_off, uint64_t lo, uint64_t hi,
-                                uint32_t* max_k, uint64_t* max_v)
-{
-    for (uint64_t i = lo; i < hi; ++i) {
-        const uint32_t kl = key_off[i + 1] - key_off[i];
-        const uint64_t vl = val_off[i + 1] - val_off[i];
-        if (kl > *max_k) *max_k = kl;
-        if (vl > *max_v) *max_v = vl;
-        if (i + 1 < hi) {
-            const uint32_t kn = key_off[i + 2] - key_off[i + 1];
-            if (kl <= kn && memcmp(keys + key_off[i], keys + key_off[i + 1], kl) == 0) return 0; // prefix (or duplicate)
-        }
-    }
-    return 1;
-}
-static uint32_t stride_from(uint32_t max_k, uint64_t max_v, uint64_t n)
-{
-    if (max_k > 64 || max_v > 3072) return 0;
-    const uint32_t stride = (uint32_t)((max_v + max_k + 16 + 15) & ~15ull);
-    return (uint64_t)stride * n <= (1ull << 31) ? stride : 0;
-}
-
 // ------------------------------------------------------------------------------------------------
 // M
 // ------------------------------------------------------------------------------------------------
@@ -646,15 +642,11 @@ extern "C" int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const
     if (n == 0) { memcpy(out_root, EMPTY, 32); return PHANT_GPU_OK; }
     cudaStream_t s = ctx->stream;
     const uint8_t* d_keys = keys; const uint32_t* d_koff = key_off; const uint8_t* d_vals = vals; const uint64_t* d_voff = val_off;
-    uint32_t leaf_stride = 0;
     if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS)) {
         for (uint64_t i = 0; i < n; ++i)
             if (key_off[i + 1] < key_off[i] || val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
         const uint64_t kb = key_off[n], vb = val_off[n];
         if ((kb && !keys) || (vb && !vals)) return PHANT_GPU_E_INVALID;
-        uint32_t max_k = 0;
-        uint64_t max_v = 0;
-        if (leaf_stride_for(keys, key_off, val_off, 0, n, &max_k, &max_v)) leaf_stride = stride_from(max_k, max_v, n);
         RC(ctx->d_msgs.reserve(ctx, kb + vb + 128));
         RC(ctx->d_off.reserve(ctx, 4 * (n + 1) + 8 * (n + 1) + 16));
         uint8_t* dk = (uint8_t*)ctx->d_msgs.ptr;
@@ -673,7 +665,7 @@ extern "C" int phant_gpu_mpt_root(phant_gpu_ctx* ctx, const uint8_t* keys, const
     CU(cudaMemcpyAsync(ctx->d_first.ptr, seg, 8, cudaMemcpyHostToDevice, s));
     RC(ctx->d_roots.reserve(ctx, 32));
     RC(ctx->build_forest(d_keys, d_koff, d_vals, d_voff, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr,
-                         leaf_stride));
+                         /*layout decided on the device*/ -1));
     CU(cudaMemcpyAsync(out_root, ctx->d_roots.ptr, 32, cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += 32;
     CU(cudaStreamSynchronize(s));
@@ -695,11 +687,6 @@ extern "C" int phant_gpu_mpt_roots(phant_gpu_ctx* ctx, const uint8_t* keys, cons
         if (key_off[i + 1] < key_off[i] || val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
     const uint64_t kb = n ? key_off[n] : 0, vb = n ? val_off[n] : 0;
     if ((kb && !keys) || (vb && !vals)) return PHANT_GPU_E_INVALID;
-    uint32_t leaf_stride = 0, max_k = 0;
-    uint64_t max_v = 0;
-    bool slot_ok = n > 0;
-    for (uint64_t t = 0; slot_ok && t < n_tries; ++t) slot_ok = leaf_stride_for(keys, key_off, val_off, seg_off[t], seg_off[t + 1], &max_k, &max_v) != 0;
-    if (slot_ok) leaf_stride = stride_from(max_k, max_v, n);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     // segment id of every key (the sortedness check must not compare across tries)
@@ -726,7 +713,7 @@ extern "C" int phant_gpu_mpt_roots(phant_gpu_ctx* ctx, const uint8_t* keys, cons
     if (n) CU(cudaMemcpyAsync(dsok, seg_of_key.data(), 4 * n, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s)); // seg_of_key is a local vector: the copy must finish before it goes out of scope
     ctx->stats.h2d_bytes += kb + vb + 16 * (n + 1) + 4 * (n_tries + 1);
-    RC(ctx->build_forest(dk, dko, dv, dvo, (uint32_t)n, dseg, (uint32_t)n_tries, dsok, (uint8_t*)ctx->d_roots.ptr, leaf_stride));
+    RC(ctx->build_forest(dk, dko, dv, dvo, (uint32_t)n, dseg, (uint32_t)n_tries, dsok, (uint8_t*)ctx->d_roots.ptr, -1));
     CU(cudaMemcpyAsync(out_roots, ctx->d_roots.ptr, 32 * n_tries, cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += 32 * n_tries;
     CU(cudaStreamSynchronize(s));
