@@ -203,3 +203,27 @@ def test_resident_trie_full_size(ctx, oracle):
     flat = np.ascontiguousarray(keys.reshape(-1))
     assert t.update(flat, v, voff, n) == o.update(flat, vals)
     t.close()
+
+
+def test_fuzz_many_tries_one_forest(ctx, oracle):
+    """400 random tries (prefix-heavy keys, empty / tiny / large values, empty and single-key tries) built as ONE forest by
+    phant_gpu_mpt_roots and each compared with the oracle; covers both arena layouts (prefix keys force the general one)."""
+    rng = np.random.default_rng(99)
+    for prefixy in (True, False):
+        lists = []
+        for _ in range(200):
+            n = int(rng.choice([0, 1, 2, 3, 7, 20, 60, 150]))
+            if prefixy:
+                kv = random_prefixy_items(rng, n) if n else []
+            else:
+                keys = sorted({rng.integers(0, 256, 8, dtype=np.uint8).tobytes() for _ in range(n)})
+                kv = [(k, rng.integers(0, 256, int(rng.choice([0, 1, 31, 32, 33, 200, 700])), dtype=np.uint8).tobytes()) for k in keys]
+            lists.append(kv)
+        flat = [x for l in lists for x in l]
+        keys, koff = oracle_lib.csr([k for k, _ in flat], np.uint32)
+        vals, voff = oracle_lib.csr([v for _, v in flat], np.uint64)
+        seg = np.zeros(len(lists) + 1, np.uint32)
+        seg[1:] = np.cumsum([len(l) for l in lists])
+        got = ctx.mpt_roots(keys, koff, vals, voff, seg, len(lists))
+        for i, kv in enumerate(lists):
+            assert got[i] == oracle.mptize(kv), (prefixy, i, len(kv))
