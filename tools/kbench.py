@@ -35,8 +35,26 @@ def main():
     ap.add_argument("--which", type=int, default=2)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--variants", default="staged,staged_nobin,direct,direct_nobin,warp")
+    ap.add_argument("--uniform", type=int, default=0, help="hash-only line over N random messages of this many bytes (SURVEY 8d: 532 and 112)")
     a = ap.parse_args()
     ctx = gpu.Context(0)
+    if a.uniform:
+        size, n = a.uniform, a.n
+        g = torch.Generator(device="cuda").manual_seed(1)
+        data = torch.randint(0, 256, (n * size + 64,), dtype=torch.uint8, device="cuda", generator=g)
+        off = torch.arange(0, n + 1, dtype=torch.int64, device="cuda") * size
+        out = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+        ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+        for it in range(a.iters + 1):
+            if it == 1:
+                ctx.reset_stats()
+            ctx.keccak256_batch(data, off, n, out)
+            ctx.synchronize()
+        s = ctx.stats()
+        ms = s["keccak_ms"] / a.iters
+        print(json.dumps({"uniform_bytes": size, "n": n, "keccak_ms": round(ms, 4), "mh_s": round(n / ms / 1e3, 1),
+                          "gperm_s": round(s["keccak_perms"] / a.iters / ms / 1e6, 3), "algorithmic_gb_s": round(n * (size + 32) / ms / 1e6, 1)}), flush=True)
+        return
     t = gen(ctx, a.which, a.n)
     digests = torch.empty((t["n_nodes"], 32), dtype=torch.uint8, device="cuda")
     status = torch.empty(a.n, dtype=torch.uint8, device="cuda")
