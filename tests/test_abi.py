@@ -58,3 +58,14 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("oracle/synth.c", "").replace("oracle/verify.c", ""), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """gcc -std=c99 -pedantic on the header, link against the library, run: NO_DEVICE here, a real hash on a GPU box."""
+    import subprocess
+    lib = os.path.join(ROOT, "phant_b200", "lib")
+    exe = str(tmp_path / "abi_c99_check")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "abi_c99_check.c"), f"-L{lib}",
+                    "-lphantgpu", f"-Wl,-rpath,{lib}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
