@@ -160,14 +160,16 @@ __device__ __forceinline__ void absorb_full_smem(uint64_t (&st)[25], uint32_t sa
     }
     keccak_f1600<UNROLL>(st);
 }
-// last block: rem < 136 message bytes at `sa`, then the 0x01 .. 0x80 padding.  Reads at most 4 bytes past the
-// message (inside the slot or its 16-byte tail pad); whatever is read beyond `rem` is masked off.
+// last block: rem < 136 message bytes at `sa`.  The 0x01 .. 00 .. 0x80 padding is WRITTEN INTO THE SLOT (stores go to the
+// idle LSU pipe) and the block is then absorbed like a full one: no per-word masks or predicates on the ALU pipe, which
+// is the pipe this kernel is bound by.  The slot is private to the lane, the block ends inside it (skew + 4*136 <= 559).
+__device__ __forceinline__ void sts32_(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+// The same block with the padding applied in registers (masks): used when the 136-byte block would not fit behind `sa`
+// inside the lane's slot (a message whose last few bytes follow four full blocks of the window).
 template <int UNROLL>
-__device__ __forceinline__ void absorb_final_smem(uint64_t (&st)[25], uint32_t sa, uint32_t rem)
+__device__ __forceinline__ void absorb_final_smem_masked(uint64_t (&st)[25], uint32_t sa, uint32_t rem)
 {
     const uint32_t a4 = sa & ~3u, sh = (sa & 3u) * 8;
-    // words [0, nfw) are whole message words, word nfw holds the last `tail` bytes and the 0x01 pad, the rest is zero:
-    // only the boundary word needs a mask, so everything else is a predicated load + funnel + xor
     const uint32_t nfw = rem >> 2, tail = rem & 3u;
     const uint32_t bmask = (1u << (8 * tail)) - 1u, pad = 1u << (8 * tail);
     uint32_t prev = rem ? lds32(a4) : 0;
@@ -184,6 +186,22 @@ __device__ __forceinline__ void absorb_final_smem(uint64_t (&st)[25], uint32_t s
         st[j >> 1] ^= (j & 1) ? ((uint64_t)word << 32) : (uint64_t)word;
     }
     keccak_f1600<UNROLL>(st);
+}
+// `room` = bytes from `sa` to the end of the lane's slot
+template <int UNROLL>
+__device__ __forceinline__ void absorb_final_smem(uint64_t (&st)[25], uint32_t sa, uint32_t rem, uint32_t room)
+{
+    if (room < KECCAK_RATE + 4) { absorb_final_smem_masked<UNROLL>(st, sa, rem); return; }
+    const uint32_t a4 = sa & ~3u, s = sa & 3u;
+    const uint32_t p0 = rem + s, p1 = KECCAK_RATE - 1 + s;      // byte positions (from a4) of the 0x01 and the 0x80
+    const uint32_t q0 = p0 >> 2, b0 = p0 & 3u, q1 = p1 >> 2, b1 = p1 & 3u;
+    uint32_t w0 = lds32(a4 + 4 * q0);
+    w0 = (w0 & ((1u << (8 * b0)) - 1u)) | (1u << (8 * b0));     // keep the message bytes below, 0x01, zeros above
+    if (q0 == q1) w0 |= 0x80u << (8 * b1);                      // rem == 135 (or the same word): 0x01 and 0x80 meet
+    sts32_(a4 + 4 * q0, w0);
+    for (uint32_t q = q0 + 1; q < q1; ++q) sts32_(a4 + 4 * q, 0u);
+    if (q1 > q0) sts32_(a4 + 4 * q1, 0x80u << (8 * b1));        // bytes above b1 lie past the block and are never used
+    absorb_full_smem<UNROLL>(st, sa);
 }
 
 // Whole-message Keccak-256 from global or shared memory (generic pointer), any alignment.

@@ -196,7 +196,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
                     sa += KECCAK_RATE;
                 }
                 if (avail == need) { // the message ends inside this window: pad and finish
-                    absorb_final_smem<UNROLL>(st, sa, (uint32_t)(avail - (uint64_t)nfull * KECCAK_RATE));
+                    absorb_final_smem<UNROLL>(st, sa, (uint32_t)(avail - (uint64_t)nfull * KECCAK_RATE), slot_s + SLOT - sa);
                     done = true;
                 } else {
                     cur += (uint64_t)nfull * KECCAK_RATE;

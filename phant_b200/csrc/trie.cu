@@ -1196,7 +1196,7 @@ frontier_branch_kernel(const uint8_t* __restrict__ child_level, const uint32_t* 
         absorb_full_smem<2>(st, slot);
         absorb_full_smem<2>(st, slot + 136);
         absorb_full_smem<2>(st, slot + 272);
-        absorb_final_smem<2>(st, slot + 408, 532 - 408);
+        absorb_final_smem<2>(st, slot + 408, 532 - 408, FR_SLOT - 408);
         uint4* o = reinterpret_cast<uint4*>(level + 32ull * p);
         o[0] = make_uint4((uint32_t)st[0], (uint32_t)(st[0] >> 32), (uint32_t)st[1], (uint32_t)(st[1] >> 32));
         o[1] = make_uint4((uint32_t)st[2], (uint32_t)(st[2] >> 32), (uint32_t)st[3], (uint32_t)(st[3] >> 32));
@@ -1243,7 +1243,7 @@ frontier_leaf_kernel(const uint8_t* __restrict__ keys32, const uint8_t* __restri
         for (int q = 0; q < 25; ++q) st[q] = 0;
         uint32_t at = slot, rem = len;
         while (rem >= 136) { absorb_full_smem<2>(st, at); at += 136; rem -= 136; }
-        absorb_final_smem<2>(st, at, rem);
+        absorb_final_smem<2>(st, at, rem, slot + FR_SLOT - at);
         uint4* o = reinterpret_cast<uint4*>(leaf_level + 32ull * pos);
         o[0] = make_uint4((uint32_t)st[0], (uint32_t)(st[0] >> 32), (uint32_t)st[1], (uint32_t)(st[1] >> 32));
         o[1] = make_uint4((uint32_t)st[2], (uint32_t)(st[2] >> 32), (uint32_t)st[3], (uint32_t)(st[3] >> 32));
