@@ -118,6 +118,15 @@ typedef struct {
 } phant_gpu_accounts;
 int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts* accounts, uint8_t out_root[32]);
 
+/* S, sharded across GPUs by the top nibble of keccak(addr): for the accounts handed in, out_roots[v] =
+ * hash of the subtree hanging under slot v of the ROOT branch (tries built from key nibble 1 on), bit v of *out_mask set
+ * when slot v is populated (unpopulated slots are zero-filled).  Each rank passes the accounts whose top nibble it owns;
+ * after one all-gather of 16 x 32 bytes + the masks, every rank hashes the root branch rlp([ref_0 .. ref_15, ""])
+ * itself (one K call).  With fewer than two populated slots overall the root is not a branch: the caller falls back to
+ * phant_gpu_state_root on the one rank that holds every account.  An account leaf is >= 70 bytes, so a populated slot's
+ * reference is always a hash (mpt.zig:104,112 inlining cannot apply). */
+int phant_gpu_state_subtree_roots(phant_gpu_ctx* ctx, const phant_gpu_accounts* accounts, uint8_t out_roots[16 * 32], uint32_t* out_mask);
+
 /* V -- batched Merkle-Patricia proof verification: the body of the TODO at
  * src/engine_api/execution_payload.zig:177-178.  Proof p = nodes [proof_first[p], proof_first[p+1]),
  * root first; node j = nodes[node_off[j] .. node_off[j+1]).  n_roots == 1 broadcasts one root.

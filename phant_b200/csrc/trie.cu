@@ -157,14 +157,15 @@ __global__ void check_sorted_kernel(Keys k, const uint64_t* __restrict__ val_off
 }
 
 // ---------------------------------------------------------------- top-down
-__global__ void init_roots_kernel(const uint32_t* __restrict__ seg_off, uint32_t n_seg, Tables t, uint32_t* counters /*[0]=units*/)
+__global__ void init_roots_kernel(const uint32_t* __restrict__ seg_off, uint32_t n_seg, Tables t, uint32_t* counters /*[0]=units*/,
+                                  uint32_t start /*nibbles already consumed above each segment's root (0 for a whole trie)*/)
 {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) {
         const uint32_t lo = seg_off[s], hi = seg_off[s + 1];
         if (hi == lo) { t.seg_root[s] = 0; continue; }
-        if (hi - lo == 1) { t.seg_root[s] = KIND_LEAF | lo; t.leaf_start[lo] = 0; continue; }
+        if (hi - lo == 1) { t.seg_root[s] = KIND_LEAF | lo; t.leaf_start[lo] = start; continue; }
         const uint32_t id = atomicAdd(&counters[0], 1u);
-        t.lo[id] = lo; t.hi[id] = hi; t.ext_from[id] = 0;
+        t.lo[id] = lo; t.hi[id] = hi; t.ext_from[id] = start;
         t.seg_root[s] = KIND_NODE | id;
     }
 }
@@ -267,12 +268,13 @@ __global__ void leaf_size_kernel(Keys k, Vals vals, Tables t, uint32_t n, uint64
 }
 // one warp per leaf: lane 0 writes the headers and the path, all lanes copy the value
 __global__ void __launch_bounds__(256)
-leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena)
+leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena,
+                   uint64_t* __restrict__ size_out /*nullable: slot layout, the encoder reports the sizes itself*/)
 {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
         const uint32_t ls = t.leaf_start[i];
-        if (ls == NONE) continue;
+        if (ls == NONE) { if (size_out && lane == 0) size_out[i] = 0; continue; }
         uint8_t* out = arena + aoff[i];
         const uint32_t nl = nlen(k, i);
         const uint32_t hpn = hp_size(nl - ls);
@@ -282,6 +284,7 @@ leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __re
         const uint64_t s_hp = str_size(hpn, hp0), s_v = str_size(vl, vl ? v[0] : 0);
         const uint32_t h = hdr_size(s_hp + s_v);
         if (lane == 0) {
+            if (size_out) size_out[i] = h + s_hp + s_v;
             put_hdr(out, s_hp + s_v, 0xc0, 0xf7);
             uint8_t* q = out + h;
             if (s_hp > hpn) q += put_hdr(q, hpn, 0x80, 0xb7);
@@ -342,13 +345,14 @@ __global__ void branch_size_kernel(Keys k, Vals vals, Tables t, uint32_t n_keys,
 // one warp per unit: lane v < 16 places child v at the prefix sum of the reference sizes, all lanes copy the value
 __global__ void __launch_bounds__(256)
 branch_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n_keys, uint32_t beg, uint32_t cnt, const uint64_t* __restrict__ aoff,
-                     const uint64_t* __restrict__ alen /*nullable: CSR*/, uint8_t* __restrict__ arena)
+                     uint64_t* __restrict__ alen /*nullable: CSR*/, bool self_size /*slot layout: compute and store alen here*/,
+                     uint8_t* __restrict__ arena)
 {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < cnt; u += (gridDim.x * blockDim.x) >> 5) {
         const uint32_t id = beg + u;
         uint8_t* out = arena + aoff[u];
-        const uint64_t total = alen ? alen[u] : aoff[u + 1] - aoff[u];
+        uint64_t total = self_size ? 0 : (alen ? alen[u] : aoff[u + 1] - aoff[u]);
         uint32_t c = 0, sz = 0, ri = 0;
         if (lane < 16) {
             c = t.child[16 * id + lane];
@@ -361,6 +365,16 @@ branch_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n_keys, uint32_t beg,
         }
         const uint32_t refs_total = __shfl_sync(0xffffffffu, pre, 15);
         const uint64_t payload_wo_value = refs_total;
+        if (self_size) {
+            uint64_t s_val = 1;
+            if (t.has_value[id]) {
+                const uint32_t i = t.lo[id];
+                const uint64_t vl = vals.off[i + 1] - vals.off[i];
+                s_val = str_size(vl, vl ? vals.bytes[vals.off[i]] : 0);
+            }
+            total = hdr_size(refs_total + s_val) + refs_total + s_val;
+            if (lane == 0) alen[u] = total;
+        }
         // total = header + payload: the header size (1..5) is the one consistent with the payload it leaves
         uint32_t hdr = 1;
         for (uint32_t cand = 1; cand <= 5; ++cand) {
@@ -398,7 +412,7 @@ __global__ void ext_size_kernel(Keys k, Tables t, uint32_t n_keys, const uint32_
     }
 }
 __global__ void ext_encode_kernel(Keys k, Tables t, uint32_t n_keys, const uint32_t* __restrict__ ids, uint32_t cnt,
-                                  const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena)
+                                  const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena, uint64_t* __restrict__ size_out /*nullable*/)
 {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
         const uint32_t id = ids[j];
@@ -407,6 +421,7 @@ __global__ void ext_encode_kernel(Keys k, Tables t, uint32_t n_keys, const uint3
         const uint64_t s_hp = str_size(hpn, hp_first_byte(k, i, from, to, false));
         const uint32_t rl = t.ref_len[n_keys + id];
         uint8_t* out = arena + aoff[j];
+        if (size_out) size_out[j] = hdr_size(s_hp + rl) + s_hp + rl;
         uint8_t* q = out + put_hdr(out, s_hp + rl, 0xc0, 0xf7);
         if (s_hp > hpn) q += put_hdr(q, hpn, 0x80, 0xb7);
         q += put_hp(q, k, i, from, to, false);
@@ -456,7 +471,7 @@ int scan_sizes(phant_gpu_ctx* ctx, uint64_t* sizes, uint64_t* offs, uint64_t cnt
 // ------------------------------------------------------------------------------------------------
 int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off,
                                 uint32_t n, const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots,
-                                int slots_hint)
+                                int slots_hint, uint32_t start_depth)
 {
     phant_gpu_ctx* ctx = this;
     cudaStream_t s = stream;
@@ -490,7 +505,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         check_sorted_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, d_val_off, d_seg_of_key, n, counters + 4);
         stats.launches++;
     }
-    init_roots_kernel<<<grid1d(device, n_seg, 256), 256, 0, s>>>(d_seg_off, n_seg, t, counters);
+    init_roots_kernel<<<grid1d(device, n_seg, 256), 256, 0, s>>>(d_seg_off, n_seg, t, counters, start_depth);
     stats.launches++;
     uint32_t h[8];
     CU(cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, s));
@@ -558,7 +573,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         RC(d_b4.reserve(ctx, 8ull * (n + 1) * 2));
         uint64_t* sizes = (uint64_t*)d_b4.ptr;
         uint64_t* offs = sizes + (n + 1);
-        leaf_size_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, vals, t, n, sizes);
+        if (!slots) leaf_size_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, vals, t, n, sizes);
         uint64_t total = (uint64_t)n * leaf_stride;
         if (slots) offs = fixed_leaf;
         else {
@@ -569,8 +584,8 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         RC(d_b5.reserve(ctx, total + 64));
         RC(d_b6.reserve(ctx, 32ull * n));
         leaf_digests = (uint8_t*)d_b6.ptr;
-        leaf_encode_kernel<<<grid1d(device, n, 256, 32), 256, 0, s>>>(k, vals, t, n, offs, (uint8_t*)d_b5.ptr);
-        stats.launches += 2;
+        leaf_encode_kernel<<<grid1d(device, n, 256, 32), 256, 0, s>>>(k, vals, t, n, offs, (uint8_t*)d_b5.ptr, slots ? sizes : nullptr);
+        stats.launches += slots ? 1 : 2;
         if (slots) RC(hash_slots((const uint8_t*)d_b5.ptr, offs, sizes, n, leaf_digests));
         else RC(hash_csr((const uint8_t*)d_b5.ptr, offs, n, total, leaf_digests));
         finalize_ref_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(n, nullptr, 0, offs, slots ? sizes : nullptr, (const uint8_t*)d_b5.ptr, leaf_digests, 0, t,
@@ -584,7 +599,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         RC(d_b7.reserve(ctx, 8ull * (lc + 1) * 2));
         uint64_t* sizes = (uint64_t*)d_b7.ptr;
         uint64_t* offs = sizes + (lc + 1);
-        branch_size_kernel<<<grid1d(device, lc, 128), 128, 0, s>>>(k, vals, t, n, lb, lc, sizes);
+        if (!slots) branch_size_kernel<<<grid1d(device, lc, 128), 128, 0, s>>>(k, vals, t, n, lb, lc, sizes);
         uint64_t total = (uint64_t)lc * BRANCH_STRIDE;
         if (slots) offs = fixed_branch;
         else {
@@ -594,8 +609,8 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         }
         RC(d_b8.reserve(ctx, total + 64));
         RC(d_b9.reserve(ctx, 32ull * lc));
-        branch_encode_kernel<<<grid1d(device, lc, 256, 32), 256, 0, s>>>(k, vals, t, n, lb, lc, offs, slots ? sizes : nullptr, (uint8_t*)d_b8.ptr);
-        stats.launches += 2;
+        branch_encode_kernel<<<grid1d(device, lc, 256, 32), 256, 0, s>>>(k, vals, t, n, lb, lc, offs, slots ? sizes : nullptr, slots, (uint8_t*)d_b8.ptr);
+        stats.launches += slots ? 1 : 2;
         if (slots) RC(hash_slots((const uint8_t*)d_b8.ptr, offs, sizes, lc, (uint8_t*)d_b9.ptr));
         else RC(hash_csr((const uint8_t*)d_b8.ptr, offs, lc, total, (uint8_t*)d_b9.ptr));
         finalize_ref_kernel<<<grid1d(device, lc, 256), 256, 0, s>>>(lc, nullptr, lb, offs, slots ? sizes : nullptr, (const uint8_t*)d_b8.ptr,
@@ -603,7 +618,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         stats.launches++;
         if (le) {
             const uint32_t* ids = t.ext_list + lb;
-            ext_size_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, sizes);
+            if (!slots) ext_size_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, sizes);
             total = (uint64_t)le * EXT_STRIDE;
             offs = sizes + (lc + 1);
             if (slots) offs = fixed_ext;
@@ -613,8 +628,8 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
                 CU(cudaStreamSynchronize(s));
             }
             RC(d_b8.reserve(ctx, total + 64));
-            ext_encode_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, offs, (uint8_t*)d_b8.ptr);
-            stats.launches += 2;
+            ext_encode_kernel<<<grid1d(device, le, 128), 128, 0, s>>>(k, t, n, ids, le, offs, (uint8_t*)d_b8.ptr, slots ? sizes : nullptr);
+            stats.launches += slots ? 1 : 2;
             if (slots) RC(hash_slots((const uint8_t*)d_b8.ptr, offs, sizes, le, (uint8_t*)d_b9.ptr));
             else RC(hash_csr((const uint8_t*)d_b8.ptr, offs, le, total, (uint8_t*)d_b9.ptr));
             finalize_ref_kernel<<<grid1d(device, le, 256), 256, 0, s>>>(le, ids, 0, offs, slots ? sizes : nullptr, (const uint8_t*)d_b8.ptr,
@@ -898,14 +913,37 @@ int phant_gpu_ctx::sort_by_segment_and_hash(const uint8_t* d_hashes, const uint3
     return PHANT_GPU_OK;
 }
 
-extern "C" int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts* a, uint8_t out_root[32])
+namespace {
+// seg_off[v] = first sorted key whose top nibble is >= v (v = 0..16): the 16 subtrees under the root branch
+__global__ void top_nibble_segments_kernel(const uint8_t* __restrict__ sorted_keys32, uint32_t n, uint32_t* __restrict__ seg_off)
+{
+    const uint32_t v = threadIdx.x;
+    if (v > 16) return;
+    uint32_t a = 0, b = n;
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if ((uint32_t)(sorted_keys32[32ull * mid] >> 4) < v) a = mid + 1; else b = mid;
+    }
+    seg_off[v] = a;
+}
+} // namespace
+
+// S and its sharded form.  subtree_mask == nullptr: out = the state root (32 bytes).  Otherwise: out = 16 x 32 bytes, the
+// hashes of the subtrees under the root branch's 16 slots (accounts grouped by the top nibble of keccak(addr), tries built
+// from nibble 1 on), *subtree_mask bit v = slot v is populated.  An account leaf is >= 70 bytes, so a populated slot's
+// reference is always the 32-byte hash.
+static int state_root_impl(phant_gpu_ctx* ctx, const phant_gpu_accounts* a, uint8_t* out_root, uint32_t* subtree_mask)
 {
     if (!ctx || !a || !out_root) return PHANT_GPU_E_INVALID;
     if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) return PHANT_GPU_E_INVALID; // S takes host tables (it is the StateDB flattening)
     const uint64_t n = a->n_accounts;
     static const uint8_t EMPTY[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
                                       0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
-    if (n == 0) { memcpy(out_root, EMPTY, 32); return PHANT_GPU_OK; }
+    if (n == 0) {
+        if (subtree_mask) { *subtree_mask = 0; memset(out_root, 0, 16 * 32); }
+        else memcpy(out_root, EMPTY, 32);
+        return PHANT_GPU_OK;
+    }
     if (n >= (1ull << 30) || !a->addr20 || !a->nonce || !a->balance32 || !a->code_off || !a->slot_off) return PHANT_GPU_E_INVALID;
     for (uint64_t i = 0; i < n; ++i)
         if (a->code_off[i + 1] < a->code_off[i] || a->slot_off[i + 1] < a->slot_off[i]) return PHANT_GPU_E_INVALID;
@@ -1024,16 +1062,45 @@ extern "C" int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts
     account_fill_kernel<<<grid1d(dev, n + 1, 256), 256, 0, s>>>((const uint64_t*)(in + o_nonce), in + o_bal, sroots, hb + h_code, hb + h_addr, acc_perm,
                                                                (uint32_t)n, avo, ak, ako, av);
     ctx->stats.launches++;
+    RC(ctx->d_first.reserve(ctx, 128));
+    RC(ctx->d_roots.reserve(ctx, 16 * 32));
+    if (subtree_mask) {
+        uint32_t seg[17];
+        top_nibble_segments_kernel<<<1, 32, 0, s>>>(ak, (uint32_t)n, (uint32_t*)ctx->d_first.ptr);
+        ctx->stats.launches++;
+        CU(cudaMemcpyAsync(seg, ctx->d_first.ptr, sizeof seg, cudaMemcpyDeviceToHost, s));
+        RC(ctx->build_forest(ak, ako, av, avo, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 16, nullptr, (uint8_t*)ctx->d_roots.ptr,
+                             160, /*the root branch consumed nibble 0*/ 1));
+        CU(cudaMemcpyAsync(out_root, ctx->d_roots.ptr, 16 * 32, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += 16 * 32 + sizeof seg;
+        CU(cudaStreamSynchronize(s));
+        uint32_t mask = 0;
+        for (int v = 0; v < 16; ++v) {
+            if (seg[v + 1] > seg[v]) mask |= 1u << v;
+            else memset(out_root + 32 * v, 0, 32);
+        }
+        *subtree_mask = mask;
+        return PHANT_GPU_OK;
+    }
     uint32_t seg[2] = {0, (uint32_t)n};
-    RC(ctx->d_first.reserve(ctx, 64));
     CU(cudaMemcpyAsync(ctx->d_first.ptr, seg, 8, cudaMemcpyHostToDevice, s));
-    RC(ctx->d_roots.reserve(ctx, 32));
     RC(ctx->build_forest(ak, ako, av, avo, (uint32_t)n, (const uint32_t*)ctx->d_first.ptr, 1, nullptr, (uint8_t*)ctx->d_roots.ptr,
                          /*32-byte keys, account RLP <= 110 B*/ 160));
     CU(cudaMemcpyAsync(out_root, ctx->d_roots.ptr, 32, cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += 32;
     CU(cudaStreamSynchronize(s));
     return PHANT_GPU_OK;
+}
+
+extern "C" int phant_gpu_state_root(phant_gpu_ctx* ctx, const phant_gpu_accounts* a, uint8_t out_root[32])
+{
+    return state_root_impl(ctx, a, out_root, nullptr);
+}
+
+extern "C" int phant_gpu_state_subtree_roots(phant_gpu_ctx* ctx, const phant_gpu_accounts* a, uint8_t out_roots[16 * 32], uint32_t* out_mask)
+{
+    if (!out_mask) return PHANT_GPU_E_INVALID;
+    return state_root_impl(ctx, a, out_roots, out_mask);
 }
 
 // ------------------------------------------------------------------------------------------------

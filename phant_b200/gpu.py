@@ -55,7 +55,7 @@ class TrieDesc(C.Structure):
 EXPORTS = [
     "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_set_stream", "phant_gpu_strerror",
     "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
-    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
+    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
 ]
@@ -89,6 +89,7 @@ def _lib():
     L.phant_gpu_mpt_root.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_mpt_roots.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_state_root.argtypes = [vp, C.POINTER(Accounts), vp]
+    L.phant_gpu_state_subtree_roots.argtypes = [vp, C.POINTER(Accounts), vp, C.POINTER(C.c_uint32)]
     L.phant_gpu_verify_proofs.argtypes = [vp, C.POINTER(ProofBatch), vp, vp, vp, vp]
     L.phant_gpu_verify_witness.argtypes = [vp, C.POINTER(Witness), vp, vp, vp, vp]
     L.phant_gpu_logs_bloom.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64, vp]
@@ -183,6 +184,15 @@ class Context:
         out = np.zeros(32, np.uint8)
         self._chk(_lib().phant_gpu_state_root(self._h, C.byref(a), _ptr(out)), "state_root")
         return out.tobytes()
+
+    def state_subtree_roots(self, n, addr20, nonce, balance32, code, code_off, slot_keys32, slot_vals32, slot_off):
+        """(16 x 32 uint8 subtree hashes under the root branch, populated-slot mask) of the accounts handed in"""
+        a = Accounts(n, _ptr(addr20), _ptr(nonce), _ptr(balance32), _ptr(code), _ptr(code_off), _ptr(slot_keys32),
+                     _ptr(slot_vals32), _ptr(slot_off))
+        out = np.zeros((16, 32), np.uint8)
+        mask = C.c_uint32(0)
+        self._chk(_lib().phant_gpu_state_subtree_roots(self._h, C.byref(a), _ptr(out), C.byref(mask)), "state_subtree_roots")
+        return out, int(mask.value)
 
     # V
     def verify_proofs(self, n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, bitmap=None, status=None,

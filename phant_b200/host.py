@@ -148,21 +148,61 @@ class StateDB:
 
     def root(self, ctx):
         accts = sorted(self.db.items())
-        n = len(accts)
-        one = np.zeros(1, np.uint8)
-        addr = np.frombuffer(b"".join(a for a, _ in accts), np.uint8) if n else one
-        nonce = np.array([s.nonce for _, s in accts], np.uint64) if n else np.zeros(1, np.uint64)
-        bal = np.frombuffer(b"".join(s.balance.to_bytes(32, "big") for _, s in accts), np.uint8) if n else one
-        code, coff = _csr([s.code for _, s in accts], np.uint64)
-        sk, sv, soff = [], [], [0]
-        for _, s in accts:
-            for k, v in s.storage.items():
-                sk.append(int(k).to_bytes(32, "big"))
-                sv.append(int(v).to_bytes(32, "big"))
-            soff.append(len(sk))
-        skeys = np.frombuffer(b"".join(sk), np.uint8) if sk else one
-        svals = np.frombuffer(b"".join(sv), np.uint8) if sv else one
-        return ctx.state_root(n, addr, nonce, bal, code, coff, skeys, svals, np.array(soff, np.uint64))
+        return ctx.state_root(len(accts), *_flatten_accounts(accts))
+
+    # ---- the same root with the account trie sharded over GPUs by top nibble ----
+    def hashed_top_nibbles(self, ctx):
+        """(sorted account list, top nibble of keccak(address) per account): which root-branch slot each account is under"""
+        accts = sorted(self.db.items())
+        if not accts:
+            return accts, np.zeros(0, np.uint8)
+        h = keccak256_batch(ctx, [a for a, _ in accts])
+        return accts, np.array([x[0] >> 4 for x in h], np.uint8)
+
+    def local_subtree_roots(self, ctx, rank, world):
+        """this rank's share: (16 x 32 subtree hashes, mask, accounts it holds) for the root-branch slots it owns"""
+        from . import shard
+        accts, nib = self.hashed_top_nibbles(ctx)
+        mine = [accts[i] for i in range(len(accts)) if shard.nibble_owner(int(nib[i]), world) == rank]
+        refs, mask = ctx.state_subtree_roots(len(mine), *_flatten_accounts(mine))
+        return refs, mask, mine
+
+    def root_sharded(self, ctx, rank, world, group=None):
+        """StateDB.root() over `world` GPUs: every rank holds the same StateDB (phant's state lives on the host), builds the
+        subtrees of its own top nibbles, ONE all-reduce of 16 x 32 bytes + presence flags, and every rank hashes the root
+        branch itself.  Equals root() bit for bit."""
+        from . import shard
+        refs, mask, mine = self.local_subtree_roots(ctx, rank, world)
+        refs_all, mask_all = shard.allgather_subtree_roots(refs, mask, group)
+        if bin(mask_all).count("1") >= 2:
+            return keccak256(ctx, shard.root_branch_rlp(refs_all, mask_all))
+        # zero or one populated slot: the root is empty / a leaf / an extension, not a branch; the one rank that owns the
+        # slot holds every account and computes the whole root, the others contribute zeros to a second 32-byte reduce
+        full = np.zeros(32, np.uint8)
+        if mask_all == 0:
+            full = np.frombuffer(ctx.state_root(0, *_flatten_accounts([])), np.uint8).copy() if rank == 0 else full
+        elif mask:
+            full = np.frombuffer(ctx.state_root(len(mine), *_flatten_accounts(mine)), np.uint8).copy()
+        return shard.sum_bytes(full, group).tobytes()
+
+
+def _flatten_accounts(accts):
+    """[(address, AccountState)] -> the SoA / CSR tables of phant_gpu_accounts (include/phant_gpu.h)"""
+    n = len(accts)
+    one = np.zeros(1, np.uint8)
+    addr = np.frombuffer(b"".join(a for a, _ in accts), np.uint8) if n else one
+    nonce = np.array([s.nonce for _, s in accts], np.uint64) if n else np.zeros(1, np.uint64)
+    bal = np.frombuffer(b"".join(s.balance.to_bytes(32, "big") for _, s in accts), np.uint8) if n else one
+    code, coff = _csr([s.code for _, s in accts], np.uint64)
+    sk, sv, soff = [], [], [0]
+    for _, s in accts:
+        for k, v in s.storage.items():
+            sk.append(int(k).to_bytes(32, "big"))
+            sv.append(int(v).to_bytes(32, "big"))
+        soff.append(len(sk))
+    skeys = np.frombuffer(b"".join(sk), np.uint8) if sk else one
+    svals = np.frombuffer(b"".join(sv), np.uint8) if sv else one
+    return addr, nonce, bal, code, coff, skeys, svals, np.array(soff, np.uint64)
 
 
 def run_block_post_checks(ctx, header, encoded_txs, encoded_receipts, encoded_withdrawals, statedb=None):
@@ -282,3 +322,82 @@ def verify_witness(ctx, state_root, proofs):
     bitmap = np.zeros((n + 63) // 64, np.uint64)
     ctx.verify_proofs(n, nodes, node_off, first, keys, root, 1, bitmap, status, None, None)
     return status.tolist()
+
+
+# ---- the witness wire format ------------------------------------------------------------------------------
+# The reference carries the witness as an opaque byte string whose layout it leaves undefined
+# (src/engine_api/execution_payload.zig:20-34 `witness: []const u8`, TODO at :177-178).  This mirror reads the layout geth's
+# stateless mode puts on the wire -- rlp([headers, codes, state]), `state` the unordered set of trie nodes -- with strict,
+# canonical RLP (the same rules the proof walk applies to nodes); anything else raises InvalidWitness.
+class InvalidWitness(ValueError):
+    pass
+
+
+def _rlp_header(b, pos, end):
+    """(is_list, payload_start, payload_end) of the item at pos; canonical encodings only"""
+    if pos >= end:
+        raise InvalidWitness("truncated item")
+    t = b[pos]
+    if t < 0x80:
+        return False, pos, pos + 1
+    short, long_ = (0x80, 0xb7) if t < 0xc0 else (0xc0, 0xf7)
+    if t <= long_:
+        start, ln = pos + 1, t - short
+        if short == 0x80 and ln == 1 and start < end and b[start] < 0x80:
+            raise InvalidWitness("single byte below 0x80 must encode itself")
+    else:
+        ll = t - long_
+        if pos + 1 + ll > end or b[pos + 1] == 0:
+            raise InvalidWitness("bad length of length")
+        ln = int.from_bytes(b[pos + 1:pos + 1 + ll], "big")
+        if ln < 56:
+            raise InvalidWitness("long form used for a short payload")
+        start = pos + 1 + ll
+    if start + ln > end:
+        raise InvalidWitness("item overruns its container")
+    return t >= 0xc0, start, start + ln
+
+
+def _rlp_list_items(b, start, end):
+    pos, out = start, []
+    while pos < end:
+        is_list, ps, pe = _rlp_header(b, pos, end)
+        out.append((is_list, pos, ps, pe))
+        pos = pe
+    return out
+
+
+def decode_witness(blob):
+    """witness bytes -> (headers: [raw rlp], codes: [bytes], nodes: [bytes]); raises InvalidWitness"""
+    b = bytes(blob)
+    is_list, ps, pe = _rlp_header(b, 0, len(b))
+    if not is_list or pe != len(b):
+        raise InvalidWitness("witness is not one RLP list")
+    fields = _rlp_list_items(b, ps, pe)
+    if len(fields) != 3 or not all(f[0] for f in fields):
+        raise InvalidWitness("witness must be [headers, codes, state]")
+    headers = []
+    for is_l, p0, _, e in _rlp_list_items(b, fields[0][2], fields[0][3]):
+        if not is_l:
+            raise InvalidWitness("header is not a list")
+        headers.append(b[p0:e])
+    out = []
+    for f in fields[1:]:
+        items = _rlp_list_items(b, f[2], f[3])
+        if any(it[0] for it in items):
+            raise InvalidWitness("code / node is not a byte string")
+        out.append([b[s:e] for _, _, s, e in items])
+    return headers, out[0], out[1]
+
+
+def encode_witness(headers, codes, nodes):
+    """inverse of decode_witness (headers already RLP-encoded)"""
+    return _rlp_list([_rlp_list(list(headers)), _rlp_list([_rlp_str(c) for c in codes]), _rlp_list([_rlp_str(n) for n in nodes])])
+
+
+def verify_payload_witness(ctx, state_root, witness_blob, hashed_keys):
+    """What newPayloadV2Handler's TODO (execution_payload.zig:177-178) asks for: decode the payload's witness and check that
+    every touched key resolves inside its node set from `state_root`.  Returns the per-key status list; raises
+    InvalidWitness for an undecodable blob.  The payload is refused unless every status is 1 or 2."""
+    _, _, nodes = decode_witness(witness_blob)
+    return verify_witness_nodes(ctx, state_root, nodes, hashed_keys)

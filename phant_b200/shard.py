@@ -5,6 +5,7 @@ Range boundaries are multiples of 64 so that accept-bitmap words are disjoint be
 SUM over int64 words equal to bitwise OR (NCCL has no bitwise reduction).  Pure host logic: works with
 torch.distributed over NCCL (GPU) or gloo (CPU tests).
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -39,3 +40,48 @@ def block_reject_counts(status, block_of_proof, n_blocks, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(rej, op=dist.ReduceOp.SUM, group=group)
     return rej
+
+
+# ---- state root sharded by the top nibble of keccak(address): 16 independent subtrees under the root branch ----
+def nibble_owner(v, world):
+    """rank that builds the subtree under root-branch slot v: contiguous slot ranges, ranks beyond 16 stay idle"""
+    return v * min(world, 16) // 16
+
+
+def _sum_over_ranks(t, group):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t = t.cpu()
+    return t
+
+
+def allgather_subtree_roots(refs, mask, group=None):
+    """refs: (16, 32) uint8 with zero rows for slots this rank does not own; mask: its populated slots.  One all-reduce
+    (SUM over disjoint slots == gather) of 16 x 32 bytes + 16 presence flags; returns (refs_all, mask_all) on every rank."""
+    t = torch.zeros(16 * 33, dtype=torch.int32)
+    t[:512] = torch.from_numpy(np.ascontiguousarray(refs, np.uint8).reshape(-1).astype(np.int32))
+    t[512:] = torch.tensor([(mask >> v) & 1 for v in range(16)], dtype=torch.int32)
+    t = _sum_over_ranks(t, group)
+    flags = t[512:].tolist()
+    assert all(f in (0, 1) for f in flags), "two ranks claimed the same root-branch slot"
+    return t[:512].numpy().astype(np.uint8).reshape(16, 32), sum(1 << v for v in range(16) if flags[v])
+
+
+def sum_bytes(b, group=None):
+    """all-reduce of a byte string that is non-zero on one rank only"""
+    t = torch.from_numpy(np.ascontiguousarray(b, np.uint8).astype(np.int32))
+    return _sum_over_ranks(t, group).numpy().astype(np.uint8)
+
+
+def root_branch_rlp(refs_all, mask_all):
+    """rlp([ref_0 .. ref_15, ""]) of the account trie's root branch (src/mpt/mpt.zig:218-247): populated slots hold the
+    32-byte subtree hash, the others and the value slot the empty string"""
+    body = b"".join((b"\xa0" + bytes(refs_all[v])) if (mask_all >> v) & 1 else b"\x80" for v in range(16)) + b"\x80"
+    n = len(body)
+    if n < 56:
+        return bytes([0xc0 + n]) + body
+    ln = n.to_bytes((n.bit_length() + 7) // 8, "big")
+    return bytes([0xf7 + len(ln)]) + ln + body

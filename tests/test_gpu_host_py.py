@@ -184,3 +184,72 @@ def test_receipts_root_reference_vector(ctx, golden):
     root, block_bloom = receipts_root(ctx, receipts)
     assert root.hex() == g["receipts_root"]
     assert receipts[0].bloom.hex() == g["bloom"] and block_bloom.hex() == g["bloom"]
+
+
+def test_state_root_sharded_by_top_nibble(ctx, oracle, golden):
+    """SURVEY.md 8e for S: the account trie split into the 16 subtrees under the root branch (phant_gpu_state_subtree_roots),
+    ranks simulated one after another on this GPU; the combined root must equal the unsharded S root and the oracle's,
+    for every world size, on random states (storage, code, lone-slot cases) and on the fixture states."""
+    import numpy as np
+    from phant_b200 import host, shard
+    from test_shard_gloo import _random_statedb
+
+    def oracle_root(db):
+        accounts = [{"address": a.hex(), "nonce": s.nonce, "balance": "%064x" % s.balance, "code": s.code.hex(),
+                     "storage": {"%064x" % k: "%064x" % v for k, v in s.storage.items()}} for a, s in sorted(db.db.items())]
+        return oracle.state_root(accounts)
+
+    def sharded(db, world):
+        refs, mask = np.zeros((16, 32), np.uint8), 0
+        for rank in range(world):
+            r, m, _ = db.local_subtree_roots(ctx, rank, world)
+            assert mask & m == 0 and not r[[v for v in range(16) if not (m >> v) & 1]].any()
+            refs, mask = refs + r, mask | m
+        return host.keccak256(ctx, shard.root_branch_rlp(refs, mask)) if bin(mask).count("1") >= 2 else None
+
+    dbs = [_random_statedb(np.random.default_rng(s), n) for s, n in ((1, 2), (2, 17), (3, 400), (4, 5000))]
+    g = golden("fixture_states.json.gz")
+    for name in list(g["tables"])[:12]:
+        db = host.StateDB()
+        for a in g["tables"][name]:
+            db.db[bytes.fromhex(a["address"])] = host.AccountState(a["nonce"], int(a["balance"], 16), bytes.fromhex(a["code"]),
+                                                                 {int(k, 16): int(v, 16) for k, v in a["storage"].items()})
+        dbs.append(db)
+    branch_rooted = 0
+    for db in dbs:
+        want = db.root(ctx)
+        assert want == oracle_root(db)
+        assert db.root_sharded(ctx, 0, 1) == want  # world 1: no process group needed
+        for world in (2, 4, 16):
+            got = sharded(db, world)
+            if got is not None:
+                assert got == want, (len(db.db), world)
+                branch_rooted += 1
+    assert branch_rooted >= 20
+    lone = _random_statedb(np.random.default_rng(9), 3, oracle)  # every account under slot 7: root is not a branch
+    assert lone.root_sharded(ctx, 0, 1) == lone.root(ctx) == oracle_root(lone)
+
+
+def test_payload_witness_blob(ctx, oracle, golden):
+    """N2: witness bytes as they would arrive in the payload (rlp([headers, codes, state]), nodes as an unordered set)
+    -> decode -> verifier; a dropped node shows as status 3, a damaged node as a missing child (3) or a reject (0)"""
+    import random
+    from helpers import secure_account_items
+    from phant_b200 import host
+    g = golden("fixture_states.json.gz")
+    accounts = max(g["tables"].values(), key=len)[:80]
+    items = secure_account_items(oracle.keccak256, oracle.mptize, accounts)
+    trie = oracle.trie(items)
+    keys = [k for k, _ in items[:50]] + [oracle.keccak256(b"nobody"), oracle.keccak256(b"nothing")]
+    nodes = list({nd: 1 for k in keys for nd in trie.prove(k)})
+    random.Random(5).shuffle(nodes)
+    blob = host.encode_witness([], [bytes.fromhex(a["code"]) for a in accounts[:3]], nodes)
+    assert host.verify_payload_witness(ctx, trie.root(), blob, keys) == [1] * 50 + [2, 2]
+    leaf = trie.prove(keys[7])[-1]
+    short = host.encode_witness([], [], [n for n in nodes if n != leaf])
+    st = host.verify_payload_witness(ctx, trie.root(), short, keys)
+    assert st[7] == 3 and all(s in (1, 2) for i, s in enumerate(st) if i != 7)
+    dmg = [bytes([n[0]]) + bytes([n[1] ^ 0x40]) + n[2:] if n == leaf else n for n in nodes]
+    assert host.verify_payload_witness(ctx, trie.root(), host.encode_witness([], [], dmg), keys)[7] in (0, 3)
+    with pytest.raises(host.InvalidWitness):
+        host.verify_payload_witness(ctx, trie.root(), blob[:-1], keys)

@@ -1,0 +1,57 @@
+"""N2: the witness wire format in front of the verifier -- host logic only, no GPU.
+rlp([headers, codes, state]); strict canonical RLP; anything else is InvalidWitness (never a silent accept)."""
+import numpy as np
+import pytest
+
+from phant_b200 import host
+
+
+def sample(rng):
+    headers = [host._rlp_list([host._rlp_str(rng.integers(0, 256, 32, dtype=np.uint8).tobytes()), host._rlp_str(b"\x01")]) for _ in range(2)]
+    codes = [b"", b"\x00", b"\x7f", b"\x80", rng.integers(0, 256, 300, dtype=np.uint8).tobytes()]
+    nodes = [rng.integers(0, 256, int(l), dtype=np.uint8).tobytes() for l in (532, 112, 83, 55, 56, 1, 70000)]
+    return headers, codes, nodes
+
+
+def test_round_trip():
+    rng = np.random.default_rng(1)
+    h, c, n = sample(rng)
+    blob = host.encode_witness(h, c, n)
+    assert host.decode_witness(blob) == (h, c, n)
+    assert host.decode_witness(host.encode_witness([], [], [])) == ([], [], [])
+    assert host.decode_witness(bytes.fromhex("c3c0c0c0")) == ([], [], [])
+
+
+@pytest.mark.parametrize("bad", [
+    "", "80", "c0", "c2c0c0", "c4c0c0c0c0",     # not a list / wrong arity
+    "c3c0c080", "c380c0c0",                      # field is a string, not a list
+    "c4c0c0c0",                                  # outer length overruns
+    "c3c0c0c000",                                # trailing byte
+    "c5c0c0c28100",                              # 0x00 must encode itself
+    "c6c0c0c3b80100",                            # long form for a 1-byte payload
+    "c7c0c0c4b9000100",                          # leading zero in the length
+    "c4c0c0c181",                                # truncated node
+    "c5c0c0c2c101",                              # node is a list
+    "c4c180c0c0",                                # header is a string
+])
+def test_malformed_is_refused(bad):
+    with pytest.raises(host.InvalidWitness):
+        host.decode_witness(bytes.fromhex(bad))
+
+
+def test_every_truncation_and_byte_flip_in_the_framing_is_refused_or_changes_the_nodes():
+    rng = np.random.default_rng(2)
+    h, c, n = sample(rng)
+    n = n[:5]
+    blob = host.encode_witness(h, c, n)
+    for cut in range(len(blob)):
+        with pytest.raises(host.InvalidWitness):
+            host.decode_witness(blob[:cut])
+    for pos in rng.integers(0, len(blob), 400):
+        mut = bytearray(blob)
+        mut[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            got = host.decode_witness(bytes(mut))
+        except host.InvalidWitness:
+            continue
+        assert got != (h, c, n)  # decodable, but then it is a different witness (the walk will judge its nodes)
