@@ -86,6 +86,26 @@ int main()
     k1[31] = 1; k2[31] = 2; v1[31] = 0xfe; v2[31] = 0xfd;
     acc.storage[k1] = v1; acc.storage[k2] = v2;
     expect(H(db2.root(g)), "d3e845156fca75de99712281581304fbde104c0fc5a102b09288c07cdde0b666", "two_accounts step 2");
+    // ---- the same root sharded over 2 / 4 / 16 ranks by top nibble: shares or-ed together, root branch hashed once ----
+    state::StateDB big;
+    for (int i = 0; i < 200; ++i) {
+        Address a{}; a[0] = (uint8_t)i; a[7] = (uint8_t)(i * 31); a[19] = (uint8_t)(i >> 1);
+        auto& s = big.db[a];
+        s.nonce = i; s.balance[31] = (uint8_t)i; s.balance[20] = 1;
+        if (i % 3 == 0) s.code = {0x60, (uint8_t)i};
+        if (i % 5 == 0) { std::array<uint8_t, 32> k{}, v{}; k[31] = (uint8_t)i; v[15] = 7; s.storage[k] = v; }
+    }
+    const std::string big_root = H(big.root(g));
+    for (int world : {1, 2, 4, 16}) {
+        state::StateDB::SubtreeRoots all;
+        for (int r = 0; r < world; ++r) {
+            const auto part = big.subtreeRoots(g, r, world);
+            if (all.mask & part.mask) expect("overlap", "disjoint", "subtree ownership");
+            all.mask |= part.mask;
+            for (size_t b = 0; b < all.refs.size(); ++b) all.refs[b] |= part.refs[b];
+        }
+        expect(H(state::StateDB::rootFromSubtreeRoots(g, all)), big_root, ("sharded StateDB.root world " + std::to_string(world)).c_str());
+    }
     // ---- witness: an absent key under the empty root, and a bogus chain ----
     engine_api::Witness w;
     Hash32 key{};

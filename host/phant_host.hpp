@@ -7,6 +7,7 @@
 //   blockchain::calculateMPTRoot                  src/blockchain/blockchain.zig:209-235
 //   engine_api::payloadListRoot                   src/engine_api/execution_payload.zig:125-139 (32-byte BE index keys)
 //   state::StateDB::root                          hook src/blockchain/blockchain.zig:83-85 (missing in the reference)
+//   state::StateDB::subtreeRoots / rootFromSubtreeRoots   the same root sharded over GPUs by top nibble
 //   engine_api::verifyWitness                     hook src/engine_api/execution_payload.zig:177-178 (TODO in the reference)
 //
 // No arithmetic happens here: every hash and every root comes from libphantgpu.so.  Errors from the library
@@ -134,6 +135,21 @@ inline Bytes encode_uint(uint64_t v)
     out.insert(out.end(), be.begin(), be.end());
     return out;
 }
+// list header in front of an already concatenated payload
+inline Bytes wrap_list(const Bytes& payload)
+{
+    Bytes out;
+    if (payload.size() < 56) out.push_back((uint8_t)(0xc0 + payload.size()));
+    else {
+        Bytes be;
+        for (int s = 56; s >= 0; s -= 8)
+            if (!be.empty() || ((uint64_t)payload.size() >> s) & 0xff) be.push_back((uint8_t)((uint64_t)payload.size() >> s));
+        out.push_back((uint8_t)(0xf7 + be.size()));
+        out.insert(out.end(), be.begin(), be.end());
+    }
+    out.insert(out.end(), payload.begin(), payload.end());
+    return out;
+}
 } // namespace rlp
 
 namespace blockchain {
@@ -170,30 +186,75 @@ public:
     // the body of the check commented out at src/blockchain/blockchain.zig:83-85
     Hash32 root(Gpu& g) const
     {
-        const size_t n = db.size();
-        Bytes addr, bal, code, skeys, svals;
-        std::vector<uint64_t> nonce, coff{0}, soff{0};
-        for (const auto& [a, acc] : db) {
-            addr.insert(addr.end(), a.begin(), a.end());
-            nonce.push_back(acc.nonce);
-            bal.insert(bal.end(), acc.balance.begin(), acc.balance.end());
-            code.insert(code.end(), acc.code.begin(), acc.code.end());
-            coff.push_back(code.size());
-            for (const auto& [k, v] : acc.storage) {
-                skeys.insert(skeys.end(), k.begin(), k.end());
-                svals.insert(svals.end(), v.begin(), v.end());
-            }
-            soff.push_back(skeys.size() / 32);
-        }
-        phant_gpu_accounts t{};
-        t.n_accounts = n;
-        t.addr20 = addr.data(); t.nonce = nonce.data(); t.balance32 = bal.data();
-        t.code = code.data(); t.code_off = coff.data();
-        t.slot_keys32 = skeys.data(); t.slot_vals32 = svals.data(); t.slot_off = soff.data();
+        Flat f(db, [](const Address&) { return true; });
         Hash32 r;
-        g.check(phant_gpu_state_root(g.ctx(), &t, r.data()), "StateDB.root");
+        g.check(phant_gpu_state_root(g.ctx(), &f.t, r.data()), "StateDB.root");
         return r;
     }
+
+    // ---- root() sharded over GPUs by the top nibble of keccak(address) ----
+    struct SubtreeRoots {
+        std::array<uint8_t, 16 * 32> refs{}; // hash of the subtree under root-branch slot v, zero where this rank owns nothing
+        uint32_t mask = 0;                   // populated slots
+    };
+    static int nibbleOwner(int v, int world) { return v * std::min(world, 16) / 16; }
+
+    // this rank's share: the subtrees of the root-branch slots it owns (one K call for the address hashes, one S call)
+    SubtreeRoots subtreeRoots(Gpu& g, int rank, int world) const
+    {
+        std::vector<Bytes> addrs;
+        for (const auto& [a, acc] : db) addrs.emplace_back(a.begin(), a.end());
+        const std::vector<Hash32> h = hasher::keccak256_batch(g, addrs);
+        size_t i = 0;
+        std::map<Address, int> slot;
+        for (const auto& [a, acc] : db) slot[a] = h[i++][0] >> 4;
+        Flat f(db, [&](const Address& a) { return nibbleOwner(slot[a], world) == rank; });
+        SubtreeRoots out;
+        g.check(phant_gpu_state_subtree_roots(g.ctx(), &f.t, out.refs.data(), &out.mask), "StateDB.subtreeRoots");
+        return out;
+    }
+
+    // after the all-gather (slots are disjoint between ranks, so summing / or-ing the shares is the gather): the root
+    // branch rlp([ref_0 .. ref_15, ""]) hashed with one K call.  Needs >= 2 populated slots -- otherwise the root is not
+    // a branch and the one rank that owns the populated slot holds every account: it calls root() on its share.
+    static Hash32 rootFromSubtreeRoots(Gpu& g, const SubtreeRoots& all)
+    {
+        if (__builtin_popcount(all.mask) < 2) throw std::invalid_argument("root is not a branch: use root() on the owning rank");
+        Bytes body;
+        for (int v = 0; v < 16; ++v) {
+            if ((all.mask >> v) & 1) { body.push_back(0xa0); body.insert(body.end(), all.refs.begin() + 32 * v, all.refs.begin() + 32 * v + 32); }
+            else body.push_back(0x80);
+        }
+        body.push_back(0x80);
+        return hasher::keccak256(g, rlp::wrap_list(body));
+    }
+
+private:
+    struct Flat { // the SoA / CSR tables of phant_gpu_accounts over the accounts `keep` selects
+        Bytes addr, bal, code, skeys, svals;
+        std::vector<uint64_t> nonce, coff{0}, soff{0};
+        phant_gpu_accounts t{};
+        template <class Keep> Flat(const std::map<Address, AccountState>& db, Keep keep)
+        {
+            for (const auto& [a, acc] : db) {
+                if (!keep(a)) continue;
+                addr.insert(addr.end(), a.begin(), a.end());
+                nonce.push_back(acc.nonce);
+                bal.insert(bal.end(), acc.balance.begin(), acc.balance.end());
+                code.insert(code.end(), acc.code.begin(), acc.code.end());
+                coff.push_back(code.size());
+                for (const auto& [k, v] : acc.storage) {
+                    skeys.insert(skeys.end(), k.begin(), k.end());
+                    svals.insert(svals.end(), v.begin(), v.end());
+                }
+                soff.push_back(skeys.size() / 32);
+            }
+            t.n_accounts = nonce.size();
+            t.addr20 = addr.data(); t.nonce = nonce.data(); t.balance32 = bal.data();
+            t.code = code.data(); t.code_off = coff.data();
+            t.slot_keys32 = skeys.data(); t.slot_vals32 = svals.data(); t.slot_off = soff.data();
+        }
+    };
 };
 } // namespace state
 

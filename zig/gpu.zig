@@ -67,6 +67,14 @@ pub const Gpu = struct {
         return root;
     }
 
+    /// StateDB.root() sharded over GPUs: hashes of the 16 subtrees under the account trie's root branch for the accounts
+    /// handed in (those whose keccak(addr) top nibble this rank owns) and the mask of populated slots.
+    pub fn stateSubtreeRoots(self: *Gpu, accounts: *const c.phant_gpu_accounts, out_roots: *[16 * 32]u8) Error!u32 {
+        var mask: u32 = 0;
+        if (c.phant_gpu_state_subtree_roots(self.ctx, accounts, out_roots, &mask) != 0) return error.GpuBackend;
+        return mask;
+    }
+
     /// The body of the TODO at src/engine_api/execution_payload.zig:177-178.  Accept / reject is data.
     pub fn verifyProofs(self: *Gpu, batch: *const c.phant_gpu_proof_batch, accept_bitmap: []u64, status: ?[]u8) Error!void {
         std.debug.assert(accept_bitmap.len * 64 >= batch.n_proofs);
