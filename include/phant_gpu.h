@@ -13,7 +13,9 @@
  *   - pointers are HOST pointers and the library copies host<->device, unless the context was
  *     switched to device pointers with PHANT_GPU_FLAG_DEVICE_PTRS (benchmarks, callers that already
  *     hold witnesses in HBM).  Device-pointer inputs must be 16-byte aligned and the byte buffers
- *     (msgs / nodes) must be readable for 16 bytes past their last offset;
+ *     (msgs / nodes) must be readable for 16 bytes past their last offset.  Host inputs are
+ *     validated (monotone offsets, index ranges) before anything is launched; device-pointer inputs
+ *     are TRUSTED to be well-formed CSR -- the node CONTENTS are never trusted in either mode;
  *   - a context owns one device, one stream and its scratch memory; it is not re-entrant: one
  *     context per host thread, or lock around it (phant calls runBlock from httpz worker threads,
  *     src/main.zig:143-149);

@@ -443,7 +443,11 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         CU(cudaEventRecord(ctx->chunk_events[chunk], cs));
         CU(cudaStreamWaitEvent(s, ctx->chunk_events[chunk], 0));
         if (int rc = ctx->hash_csr(d_nodes, d_noff + n0, n1 - n0, b1 - b0, (uint8_t*)ctx->d_digests.ptr + 32 * n0,
-                                   (uint32_t*)ctx->d_summary.ptr + n0)) return rc;
+                                   (uint32_t*)ctx->d_summary.ptr + n0)) {
+            cudaStreamSynchronize(cs); // as above: no DMA on the caller's buffers after we return
+            cudaStreamSynchronize(s);
+            return rc;
+        }
         ctx->time_begin(1);
         CU(launch_walk(s, ctx->device, p1 - p0, d_nodes, d_noff, nullptr, d_pfirst + p0, (const uint8_t*)ctx->d_keys.ptr + 32 * p0,
                        (const uint8_t*)ctx->d_roots.ptr + (in->n_roots == 1 ? 0 : 32 * p0), in->n_roots, (const uint8_t*)ctx->d_digests.ptr,
