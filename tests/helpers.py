@@ -155,3 +155,45 @@ def secure_account_items(keccak, mptize, accounts):
                 rlp_str(keccak(bytes.fromhex(a["code"])))]
         items.append((keccak(bytes.fromhex(a["address"])), rlp_list(body)))
     return sorted(items)
+
+
+# ---- an independent statement of mptize (src/mpt/mpt.zig:38-119, 132-314) in plain Python: second opinion for the C oracle ----
+def _hp(nibbles, leaf):
+    """hex-prefix (mpt.zig:285-314): flag nibble 0/1 extension even/odd, 2/3 leaf even/odd"""
+    flag = 2 if leaf else 0
+    if len(nibbles) % 2:
+        nibbles = [flag + 1] + list(nibbles)
+    else:
+        nibbles = [flag, 0] + list(nibbles)
+    return bytes((nibbles[i] << 4) | nibbles[i + 1] for i in range(0, len(nibbles), 2))
+
+
+def _py_node(keccak, items, level):
+    """items: sorted [(nibble list, value)] sharing their first `level` nibbles -> the node's RLP (b"" = empty)"""
+    if not items:
+        return b""
+    if len(items) == 1:
+        return rlp_list([rlp_str(_hp(items[0][0][level:], True)), rlp_str(items[0][1])])
+    first, last = items[0][0], items[-1][0]
+    common = level
+    while common < len(first) and common < len(last) and first[common] == last[common]:
+        common += 1
+    common = min(common, len(first))  # a key that ends inside the shared run ends the extension there
+    if common > level:
+        child = _py_node(keccak, items, common)
+        return rlp_list([rlp_str(_hp(first[level:common], False)), child if len(child) < 32 else rlp_str(keccak(child))])
+    value = b""
+    if len(first) == level:
+        value, items = items[0][1], items[1:]
+    slots = []
+    for v in range(16):
+        child = _py_node(keccak, [it for it in items if it[0][level] == v], level + 1)
+        slots.append(rlp_str(b"") if not child else (child if len(child) < 32 else rlp_str(keccak(child))))
+    return rlp_list(slots + [rlp_str(value)])
+
+
+def py_mptize(keccak, kv):
+    """kv: sorted [(key bytes, value bytes)] -> root (the root node is always hashed, mpt.zig:42; empty list -> keccak(0x80))"""
+    items = [([n for b in k for n in (b >> 4, b & 15)], v) for k, v in kv]
+    node = _py_node(keccak, items, 0)
+    return keccak(node if node else b"\x80")

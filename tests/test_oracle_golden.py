@@ -154,3 +154,47 @@ def test_receipts_root_reference_vector(oracle, golden):
         rc.bloom = oracle.logs_bloom(items, [0] * len(items), 1)[0].tobytes() if items else bytes(256)
         receipts.append(rc)
     assert oracle.mptize(index_trie_items([r.encode() for r in receipts])).hex() == g["receipts_root"]
+
+
+def test_oracle_mptize_vs_independent_python(oracle, golden):
+    """the C oracle against a second, independently written statement of mpt.zig (tests/helpers.py::py_mptize): first on the
+    reference's own 7 roots (so the Python statement is itself pinned), then on random tries with prefix keys, branch
+    values, embedded children, extensions, empty and long values"""
+    import numpy as np
+    from helpers import py_mptize
+    for c in golden("mptize_kat.json")["cases"]:
+        kv = [(bytes.fromhex(k), bytes.fromhex(v)) for k, v in c["kv"]]
+        assert py_mptize(oracle.keccak256, kv).hex() == c["root"], c["name"]
+    assert py_mptize(oracle.keccak256, []) == oracle.mptize([])
+    rng = np.random.default_rng(4242)
+    for trial in range(300):
+        n = int(rng.choice([1, 2, 3, 5, 8, 20, 60]))
+        keys = set()
+        while len(keys) < n:
+            base = bytes(rng.integers(0, 3, int(rng.integers(0, 5)), dtype=np.uint8) * 17)  # nibble-repeating bytes: shared runs
+            keys.add(base + bytes(rng.integers(0, 256, int(rng.integers(0, 3)), dtype=np.uint8)))
+        kv = [(k, rng.integers(0, 256, int(rng.choice([0, 1, 1, 2, 10, 31, 32, 33, 60, 200])), dtype=np.uint8).tobytes()) for k in sorted(keys)]
+        assert py_mptize(oracle.keccak256, kv) == oracle.mptize(kv), (trial, kv)
+
+
+def test_oracle_state_root_vs_independent_python(oracle, golden):
+    """oracle_state_root (C) against keys / leaves assembled in Python and the independent py_mptize, on fixture states and
+    random ones (zero slots, empty code, big balances)"""
+    import numpy as np
+    from helpers import py_mptize, secure_account_items
+    g = golden("fixture_states.json.gz")
+    for name in list(g["tables"])[:6]:
+        acc = g["tables"][name]
+        items = secure_account_items(oracle.keccak256, lambda kv: py_mptize(oracle.keccak256, kv), acc)
+        assert py_mptize(oracle.keccak256, items) == oracle.state_root(acc), name
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        acc = []
+        for _ in range(int(rng.choice([1, 2, 9, 40]))):
+            st = {rng.integers(0, 256, 32, dtype=np.uint8).tobytes().hex(): (bytes(int(rng.integers(0, 33))) + rng.integers(0, 256, 32, dtype=np.uint8).tobytes())[:32].hex()
+                  for _ in range(int(rng.choice([0, 1, 4])))}
+            acc.append({"address": rng.integers(0, 256, 20, dtype=np.uint8).tobytes().hex(), "nonce": int(rng.choice([0, 1, 128, 2 ** 40])),
+                        "balance": "%064x" % int(rng.choice([0, 127, 128, 2 ** 255 + 5])), "code": rng.integers(0, 256, int(rng.choice([0, 1, 200])), dtype=np.uint8).tobytes().hex(),
+                        "storage": st})
+        items = secure_account_items(oracle.keccak256, lambda kv: py_mptize(oracle.keccak256, kv), acc)
+        assert py_mptize(oracle.keccak256, items) == oracle.state_root(acc), trial
