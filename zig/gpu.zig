@@ -82,6 +82,21 @@ pub const Gpu = struct {
         if (c.phant_gpu_verify_proofs(self.ctx, batch, accept_bitmap.ptr, st, null, null) != 0) return error.GpuBackend;
     }
 
+    /// The same check for a witness that is an unordered SET of trie nodes (status 3 = a node on the key's path is missing).
+    pub fn verifyWitness(self: *Gpu, witness: *const c.phant_gpu_witness, accept_bitmap: []u64, status: ?[]u8) Error!void {
+        std.debug.assert(accept_bitmap.len * 64 >= witness.n_keys);
+        const st: ?[*]u8 = if (status) |s| s.ptr else null;
+        if (c.phant_gpu_verify_witness(self.ctx, witness, accept_bitmap.ptr, st, null, null) != 0) return error.GpuBackend;
+    }
+
+    /// Many tries in one forest build: the transaction / receipt / withdrawal tries of a block or of a range of blocks
+    /// (src/blockchain/blockchain.zig:200-203).  Trie t = items [seg_off[t], seg_off[t+1]) of the CSR arrays.
+    pub fn mptRoots(self: *Gpu, keys: []const u8, key_off: []const u32, vals: []const u8, val_off: []const u64, seg_off: []const u32, out_roots: []Hash32) Error!void {
+        std.debug.assert(seg_off.len == out_roots.len + 1);
+        if (c.phant_gpu_mpt_roots(self.ctx, keys.ptr, key_off.ptr, vals.ptr, val_off.ptr, seg_off.ptr, out_roots.len, @ptrCast(out_roots.ptr)) != 0)
+            return error.GpuBackend;
+    }
+
     /// Receipt.calculateLogsBloom (src/types/receipt.zig:37-48) for all receipts of a block.
     pub fn logsBlooms(self: *Gpu, items: []const u8, item_off: []const u64, bloom_of_item: []const u32, blooms: []types.LogsBloom) Error!void {
         if (c.phant_gpu_logs_bloom(self.ctx, items.ptr, item_off.ptr, bloom_of_item.ptr, bloom_of_item.len, blooms.len, @ptrCast(blooms.ptr)) != 0)
