@@ -274,3 +274,27 @@ def test_witness_as_unordered_node_set(ctx, oracle, golden):
     status = np.zeros(len(keys), np.uint8)
     ctx.verify_witness(len(node_off) - 1, nodes, node_off, len(keys), keys32, root, 1, None, status, None, None)
     assert (status == want[0]).all() and (status[:len(items)] == 1).all() and (status[len(items):] == 2).all()
+
+
+def test_proof_kat_without_the_oracle(golden):
+    """CUDA walk against the committed vectors only (no oracle in the loop): statuses, accept bits and value slices"""
+    from phant_b200 import gpu
+    from test_oracle_proofs import batch_of, kat_batch
+    g = golden("proof_kat.json.gz")
+    proofs = kat_batch(g)
+    nodes, node_off, first, keys, roots = batch_of(proofs)
+    n = len(proofs)
+    ctx = gpu.Context(0)
+    for flags in (0, gpu.FLAG_KECCAK_DIRECT):
+        ctx.set_flags(flags)
+        bitmap = np.zeros((n + 63) // 64, np.uint64)
+        status = np.full(n, 9, np.uint8)
+        voff = np.zeros(n, np.uint64)
+        vlen = np.zeros(n, np.uint32)
+        ctx.verify_proofs(n, nodes, node_off, first, np.ascontiguousarray(keys), np.ascontiguousarray(roots), n, bitmap, status, voff, vlen)
+        for i, c in enumerate(g["cases"]):
+            assert int(status[i]) == c["status"], (flags, c["name"])
+            assert bool((int(bitmap[i // 64]) >> (i % 64)) & 1) == (c["status"] != 0), c["name"]
+            if c["status"] == 1:
+                assert nodes[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes().hex() == c["value"], c["name"]
+    ctx.close()

@@ -226,3 +226,23 @@ def test_bag_witness_matches_chain_verdicts(oracle):
     assert st3[0] in (2, 3)  # a random key leaves the materialised paths: absent if it dies in a known node, missing otherwise
     empty = np.frombuffer(bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"), np.uint8)
     assert oracle.verify_bag(nodes, node_off, k, empty)[0][0] == 2
+
+
+def kat_batch(g):
+    return [([bytes.fromhex(n) for n in c["nodes"]], bytes.fromhex(c["key"]), bytes.fromhex(c["root"])) for c in g["cases"]]
+
+
+def test_proof_kat(oracle, golden):
+    """the committed walk vectors (tests/golden/proof_kat.json.gz, made by make_proof_kat.py): oracle and Python statement
+    both reproduce every recorded status and value"""
+    g = golden("proof_kat.json.gz")
+    proofs = kat_batch(g)
+    nodes, node_off, first, keys, roots = batch_of(proofs)
+    bitmap, status, voff, vlen = oracle.verify_proofs(nodes, node_off, first, keys, roots)
+    for i, c in enumerate(g["cases"]):
+        assert int(status[i]) == c["status"], c["name"]
+        st, val = py_verify(oracle.keccak256, *proofs[i])
+        assert st == c["status"], c["name"]
+        if c["status"] == 1:
+            assert val.hex() == c["value"] == nodes[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes().hex(), c["name"]
+    assert {c["status"] for c in g["cases"]} == {0, 1, 2} and len(g["cases"]) >= 45
