@@ -69,3 +69,13 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                     "-lphantgpu", f"-Wl,-rpath,{lib}"], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
+def test_cpp_host_mirror_compiles_and_links_without_a_gpu(tmp_path):
+    """host/phant_host.hpp + host/host_test.cpp build against the header and link against the library on a machine with no
+    GPU (running them is the -m gpu test tests/test_gpu_host_cpp.py)"""
+    import subprocess
+    from phant_b200 import gpu
+    lib = os.path.dirname(gpu.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O0", "-Wall", "-Werror", "-Wno-unused-function", "-o", str(tmp_path / "host_test"),
+                    os.path.join(ROOT, "host", "host_test.cpp"), f"-L{lib}", "-lphantgpu", f"-Wl,-rpath,{lib}"], check=True)
