@@ -92,15 +92,21 @@ keccak256_direct_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
 // ------------------------------------------------------------------------------------------------
 // staged: bulk-copy engine -> per-lane shared-memory slot -> registers
 // ------------------------------------------------------------------------------------------------
-// slot = BLOCKS rate blocks + 15 bytes of skew, rounded to 16 x odd so that the 16-byte windows of a quarter warp fall
-// in distinct banks; + 16 bytes behind the last slot because the final-block reader may touch 4 bytes past a message
-constexpr int stage_slot(int blocks)
+// window = what one bulk copy brings in: BLOCKS rate blocks + 15 bytes of skew, rounded to 16 x odd so that the 16-byte
+// windows of a quarter warp fall in distinct banks.  The lane's slot is 32 bytes longer than the window (still 16 x odd):
+// the final block is padded IN the slot (absorb_final_smem), which needs 140 bytes behind the block's start; with only
+// the window, a last block that follows BLOCKS-1 full ones at a skew of 13..15 did not fit and took the masked path --
+// 3 of 16 such messages at arbitrary alignment, and because lanes of one warp then split between the two paths the warp
+// paid for both (C3: 3.93 -> 3.30 G perm/s).  + 16 bytes behind the last slot: the reader may touch 4 bytes past a message.
+constexpr int stage_window(int blocks)
 {
     int s = (blocks * KECCAK_RATE + 15 + 15) / 16;
     if (s % 2 == 0) ++s;
     return 16 * s;
 }
+constexpr int stage_slot(int blocks) { return stage_window(blocks) + 32; }
 constexpr int stage_smem(int blocks, int warps) { return 128 + warps * 32 * stage_slot(blocks) + 16; }
+static_assert(stage_smem(4, 12) <= 232448, "default shape must fit the 227 KB a CTA may opt into");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -143,7 +149,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar = smem_u32(smem) + 8 * warp;
-    constexpr int SLOT = stage_slot(BLOCKS);
+    constexpr int SLOT = stage_slot(BLOCKS), WINDOW = stage_window(BLOCKS);
     uint8_t* slot = smem + 128 + (warp * 32 + lane) * SLOT;
     const uint32_t slot_s = smem_u32(slot);
     if (lane == 0) mbar_init(bar, 32);
@@ -174,7 +180,7 @@ keccak256_staged_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __rest
             uint32_t cs = 0;
             if (need) {
                 const uint64_t span = ((end - a0) + 15) & ~(uint64_t)15;
-                cs = span < SLOT ? (uint32_t)span : SLOT;
+                cs = span < WINDOW ? (uint32_t)span : WINDOW;
                 fence_proxy_async(); // my earlier reads of the slot are ordered before the engine's writes
                 mbar_arrive_expect_tx(bar, cs);
                 bulk_g2s(slot_s, msgs + a0, cs, bar);

@@ -10,6 +10,8 @@
 // the node bytes were just streamed through L2 by the hash kernel.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace phant {
 namespace {
 
@@ -258,8 +260,10 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
     }
 }
 
-template <bool BAG>
-__global__ void __launch_bounds__(128)
+// MINB = CTAs of 128 threads the register allocator must fit per SM (8 -> <= 64 registers, 12 -> <= 40, 16 -> <= 32): the
+// walk is latency-bound (dependent loads per node), so residency is traded against spills; measured, see launch_walk
+template <bool BAG, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 walk_kernel(const Bag bag, uint64_t n_proofs, const uint8_t* __restrict__ nodes, const uint64_t* __restrict__ node_off,
             const uint64_t* __restrict__ node_index, const uint64_t* __restrict__ proof_first, const uint8_t* __restrict__ keys32,
             const uint8_t* __restrict__ roots32, uint64_t n_roots, const uint8_t* __restrict__ digests,
@@ -285,6 +289,18 @@ walk_kernel(const Bag bag, uint64_t n_proofs, const uint8_t* __restrict__ nodes,
 
 } // namespace
 
+// tuning knob (development): PHANT_WALK_MINB = 8 | 10 | 12 | 16; the default is the measured best
+static int walk_minb()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PHANT_WALK_MINB");
+        v = e ? atoi(e) : 8;
+        if (v != 10 && v != 12 && v != 16) v = 8;
+    }
+    return v;
+}
+
 cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,
                         const uint64_t* node_index, const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
                         const uint8_t* digests, const uint32_t* summary, uint64_t* bitmap, uint8_t* status, uint64_t* val_off,
@@ -294,8 +310,14 @@ cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uin
     uint64_t blocks = (n_proofs + 127) / 128;
     const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
     if (blocks > cap) blocks = cap;
-    walk_kernel<false><<<(unsigned)blocks, 128, 0, s>>>(Bag{nullptr, 0}, n_proofs, nodes, node_off, node_index, proof_first, keys32, roots32, n_roots, digests, summary,
-                                                 bitmap, status, val_off, val_len);
+#define PHANT_WALK_ARGS Bag{nullptr, 0}, n_proofs, nodes, node_off, node_index, proof_first, keys32, roots32, n_roots, digests, summary, bitmap, status, val_off, val_len
+    switch (walk_minb()) {
+    case 10: walk_kernel<false, 10><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;
+    case 12: walk_kernel<false, 12><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;
+    case 16: walk_kernel<false, 16><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;
+    default: walk_kernel<false, 8><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;
+    }
+#undef PHANT_WALK_ARGS
     return cudaGetLastError();
 }
 
@@ -336,7 +358,7 @@ cudaError_t launch_walk_bag(cudaStream_t s, int device, uint64_t n_keys, const u
     uint64_t blocks = (n_keys + 127) / 128;
     const uint64_t cap = (uint64_t)keccak_num_sms(device) * 16;
     if (blocks > cap) blocks = cap;
-    walk_kernel<true><<<(unsigned)blocks, 128, 0, s>>>(Bag{table, capacity - 1}, n_keys, nodes, node_off, nullptr, nullptr, keys32, roots32, n_roots,
+    walk_kernel<true, 8><<<(unsigned)blocks, 128, 0, s>>>(Bag{table, capacity - 1}, n_keys, nodes, node_off, nullptr, nullptr, keys32, roots32, n_roots,
                                                       digests, summary, bitmap, status, val_off, val_len);
     return cudaGetLastError();
 }
