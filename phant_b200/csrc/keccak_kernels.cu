@@ -9,7 +9,7 @@
 //                      per trip, and read back as aligned 32-bit words (one funnel shift fixes the byte
 //                      skew).  No thread ever issues a global load for message bytes, so the strided
 //                      (one-message-per-lane) access pattern never reaches the LSU as 32 uncoalesced
-//                      sectors.  One CTA of 12 warps per SM (215 KB of slots).
+//                      sectors.  One CTA of 12 warps per SM (227 KB of slots).
 //   direct             same sponge, message words loaded straight from global memory (fallback when
 //                      the buffer is not 16-byte aligned / padded; also the simplest correct kernel).
 //   warp               the layout BASELINE.json's north star describes: one WARP per sponge, lane i
@@ -21,53 +21,12 @@
 // same number of permutations.
 #include "common.cuh"
 #include "keccak_f1600.cuh"
+#include "node_summary.cuh"
 
 #include <stdlib.h>
 #include <string.h>
 
 namespace phant {
-
-// ------------------------------------------------------------------------------------------------
-// node summary for the proof walk (walk_kernel.cu): while a node's bytes sit in shared memory / L1 for hashing,
-// classify it once.  A SIMPLE BRANCH is a strictly canonical 17-item list (rule R2 of DESIGN.md) whose 16 children
-// are each empty (0x80) or a 32-byte hash (0xa0 ..) and whose value is empty -- by far the common trie node.
-// For those the walk needs no parse: summary = mask of hash children, header size, kind 1; the child for nibble n
-// sits at hdr + 33*popc(mask & ((1<<n)-1)) + (n - popc(..)).  Everything else gets summary 0 = "walk parses it".
-// The summary does not depend on the key, so it is also right for witness nodes shared between proofs.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t summarize_node(const uint8_t* p, uint32_t len)
-{
-    if (len < 18) return 0;
-    const uint32_t b0 = p[0];
-    uint32_t hdr, pay;
-    if (b0 < 0xc0) return 0;
-    if (b0 <= 0xf7) { hdr = 1; pay = b0 - 0xc0; }
-    else {
-        const uint32_t n = b0 - 0xf7;
-        if (n > 2 || p[1] == 0) return 0;
-        pay = n == 1 ? p[1] : ((uint32_t)p[1] << 8) | p[2];
-        if (pay <= 55) return 0;
-        hdr = 1 + n;
-    }
-    if (hdr + pay != len) return 0;
-    if (len == 532) { // the full branch (16 hashed children): 17 independent byte probes instead of a dependent scan
-        uint32_t ok = p[531] == 0x80;
-#pragma unroll
-        for (uint32_t i = 0; i < 16; ++i) ok &= p[3 + 33 * i] == 0xa0;
-        if (ok) return (0xffffu << 8) | (3u << 2) | 1u;
-    }
-    uint32_t o = hdr, mask = 0;
-#pragma unroll 1
-    for (uint32_t i = 0; i < 16; ++i) {
-        if (o >= len) return 0;
-        const uint32_t c = p[o];
-        if (c == 0x80) o += 1;
-        else if (c == 0xa0) { mask |= 1u << i; o += 33; }
-        else return 0;
-    }
-    if (o + 1 != len || p[o] != 0x80) return 0;
-    return (mask << 8) | (hdr << 2) | 1u;
-}
 
 // ------------------------------------------------------------------------------------------------
 // direct
