@@ -161,12 +161,16 @@ __device__ __forceinline__ void absorb_final(uint64_t (&st)[25], const MsgView& 
 // The message sits in the lane's shared-memory slot at byte address `sa` (any alignment).  Read it as aligned
 // 32-bit words (LDS.32 on the LSU pipe) and fix the byte skew with ONE funnel shift per word: 34 SHF + 34 LOP3 on
 // the ALU pipe per 136-byte block, against ~180 for the generic 64-bit path above.
+#ifndef PHANT_HOST_SMEM
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+#else // test harness (tests/hostcheck): "shared memory" is a host array, addresses are offsets into it
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; memcpy(&v, PHANT_HOST_SMEM + saddr, 4); return v; }
+#endif
 template <int UNROLL, bool DIGEST_ONLY = false>
 __device__ __forceinline__ void absorb_full_smem(uint64_t (&st)[25], uint32_t sa)
 {
@@ -186,7 +190,11 @@ __device__ __forceinline__ void absorb_full_smem(uint64_t (&st)[25], uint32_t sa
 // last block: rem < 136 message bytes at `sa`.  The 0x01 .. 00 .. 0x80 padding is WRITTEN INTO THE SLOT (stores go to the
 // idle LSU pipe) and the block is then absorbed like a full one: no per-word masks or predicates on the ALU pipe, which
 // is the pipe this kernel is bound by.  The slot is private to the lane, the block ends inside it (skew + 4*136 <= 559).
+#ifndef PHANT_HOST_SMEM
 __device__ __forceinline__ void sts32_(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+#else
+__device__ __forceinline__ void sts32_(uint32_t saddr, uint32_t v) { memcpy(PHANT_HOST_SMEM + saddr, &v, 4); }
+#endif
 // The same block with the padding applied in registers (masks): used when the 136-byte block would not fit behind `sa`
 // inside the lane's slot (a message whose last few bytes follow four full blocks of the window).
 template <int UNROLL>
