@@ -179,6 +179,17 @@ int phant_gpu_verify_witness(phant_gpu_ctx* ctx, const phant_gpu_witness* in, ui
 int phant_gpu_logs_bloom(phant_gpu_ctx* ctx, const uint8_t* items, const uint64_t* item_off, const uint32_t* bloom_of_item,
                          uint64_t n_items, uint64_t n_blooms, uint8_t* blooms);
 
+/* R -- batched sender recovery (row N4 of SURVEY.md 8f): for each i, the secp256k1 public key that signed hashes32[i]
+ * under sigs65[i] = r(32, big endian) || s(32) || recid(1), and its address keccak256(X || Y)[12..32] -- the tail of
+ * TxSigner.get_sender (src/signer/signer.zig:78-79: ecdsa_signer.erecover, src/crypto/ecdsa.zig:19-21, then
+ * hasher.keccak256(pubkey[1..])[12..]).  Decisions are those of libsecp256k1's secp256k1_ecdsa_recover, which the
+ * reference calls through zig-eth-secp256k1: ok[i] = 1 and pubkeys65[i] = 0x04 || X || Y, or ok[i] = 0 (r or s zero or
+ * >= n, recid > 3, x not on the curve, result at infinity) with zero-filled outputs.  The low-s rule and the EIP-155 `v`
+ * decoding are the caller's (signer.zig:41-76, ecdsa.zig:28-36), as in the reference.  pubkeys65 / addresses20 may be
+ * NULL.  A failed recovery is data, not an error code. */
+int phant_gpu_ecrecover_batch(phant_gpu_ctx* ctx, const uint8_t* hashes32, const uint8_t* sigs65, uint64_t n,
+                              uint8_t* pubkeys65, uint8_t* addresses20, uint8_t* ok);
+
 /* U -- resident trie + dirty-frontier root recompute (BASELINE.json "state-root recompute").
  * Round-1 shape: a complete 16-ary trie with `depth` branch levels (16^depth leaves) whose untouched
  * leaf hashes come from the synthetic PRNG; update rewrites n_dirty leaves (distinct leaf positions)

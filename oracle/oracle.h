@@ -39,6 +39,13 @@ void oracle_keccak256_batch(const uint8_t* msgs, const uint64_t* off, uint64_t n
 void oracle_logs_bloom(const uint8_t* items, const uint64_t* item_off, const uint32_t* bloom_of_item, uint64_t n_items,
                        uint64_t n_blooms, uint8_t* blooms);
 
+/* ---- secp256k1 public-key recovery (oracle/secp256k1.c): what ecdsa.Signer.erecover returns (src/crypto/ecdsa.zig:19-21,
+ * reached from TxSigner.get_sender, src/signer/signer.zig:78).  sig65 = r || s || recid.  0 = pub65 holds 0x04 || X || Y;
+ * negative = the signature recovers no key.  The arithmetic lives in libsecp256k1 behind zig-eth-secp256k1 @ 95b7f93
+ * (build.zig.zon), absent from the tree: restated from SEC 1 section 4.1.6, pinned by ecdsa.zig:38-48 and signer.zig:199-227. */
+int oracle_ecrecover(const uint8_t hash32[32], const uint8_t sig65[65], uint8_t pub65[65]);
+int oracle_secp256k1_pubkey(const uint8_t priv32[32], uint8_t pub65[65]);
+
 /* ---- mptize (follows src/mpt/mpt.zig:38-314) ----
  * keys: byte strings sorted lexicographically (a strict prefix sorts first), CSR; values CSR.
  * Returns 0, or -1 if keys are not strictly sorted (the reference asserts sortedness, mpt.zig:39). */

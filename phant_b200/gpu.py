@@ -55,7 +55,7 @@ class TrieDesc(C.Structure):
 EXPORTS = [
     "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_set_stream", "phant_gpu_strerror",
     "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
-    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
+    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_ecrecover_batch", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
 ]
@@ -90,6 +90,7 @@ def _lib():
     L.phant_gpu_mpt_roots.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_state_root.argtypes = [vp, C.POINTER(Accounts), vp]
     L.phant_gpu_state_subtree_roots.argtypes = [vp, C.POINTER(Accounts), vp, C.POINTER(C.c_uint32)]
+    L.phant_gpu_ecrecover_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp]
     L.phant_gpu_verify_proofs.argtypes = [vp, C.POINTER(ProofBatch), vp, vp, vp, vp]
     L.phant_gpu_verify_witness.argtypes = [vp, C.POINTER(Witness), vp, vp, vp, vp]
     L.phant_gpu_logs_bloom.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64, vp]
@@ -193,6 +194,11 @@ class Context:
         mask = C.c_uint32(0)
         self._chk(_lib().phant_gpu_state_subtree_roots(self._h, C.byref(a), _ptr(out), C.byref(mask)), "state_subtree_roots")
         return out, int(mask.value)
+
+    # R
+    def ecrecover_batch(self, hashes32, sigs65, n, pubkeys65=None, addresses20=None, ok=None):
+        self._chk(_lib().phant_gpu_ecrecover_batch(self._h, _ptr(hashes32), _ptr(sigs65), n, _ptr(pubkeys65), _ptr(addresses20), _ptr(ok)),
+                  "ecrecover_batch")
 
     # V
     def verify_proofs(self, n_proofs, nodes, node_off, proof_first, keys32, roots32, n_roots, bitmap=None, status=None,

@@ -401,3 +401,77 @@ def verify_payload_witness(ctx, state_root, witness_blob, hashed_keys):
     InvalidWitness for an undecodable blob.  The payload is refused unless every status is 1 or 2."""
     _, _, nodes = decode_witness(witness_blob)
     return verify_witness_nodes(ctx, state_root, nodes, hashed_keys)
+
+
+# ---- transaction senders (SURVEY.md 8f N4): TxSigner.get_sender for a whole block -------------------------------------------
+SECP256K1_N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+SPEC_TEST_CHAIN_ID = 0  # src/config/config.zig:9: legacy transactions are hashed without the EIP-155 fields on this chain
+
+
+class SenderError(ValueError):
+    """the error names of the reference: InvalidR / InvalidS (src/crypto/ecdsa.zig:28-36), EIP155_v (src/signer/signer.zig:59),
+    InvalidTransaction (undecodable), RecoveryFailed (libsecp256k1 recovers no key)"""
+
+
+def _tx_signing_parts(encoded, chain_id):
+    """one encoded transaction -> (bytes whose keccak256 is the signing hash, r, s, recid); follows TxSigner.get_sender and
+    hashTx (src/signer/signer.zig:41-188).  The unsigned fields are taken as the raw RLP items of the encoded transaction:
+    for a canonical encoding that is byte-identical to re-serialising the decoded fields, which is what the reference does."""
+    b = bytes(encoded)
+    try:
+        typed = len(b) > 0 and b[0] in (1, 2)
+        body = b[1:] if typed else b
+        is_list, ps, pe = _rlp_header(body, 0, len(body))
+        if not is_list or pe != len(body):
+            raise InvalidWitness("not one list")
+        items = _rlp_list_items(body, ps, pe)
+    except InvalidWitness as e:
+        raise SenderError("InvalidTransaction") from e
+    want = {False: 9, True: 11 if b[:1] == b"\x01" else 12}[typed]
+    if len(items) != want or any(it[0] for it in items[-3:]):
+        raise SenderError("InvalidTransaction")
+    v, r, s = (int.from_bytes(body[it[2]:it[3]], "big") for it in items[-3:])
+    if r > SECP256K1_N:                 # ecdsa.zig:29 (r == n passes here and fails in the recovery, as in the reference)
+        raise SenderError("InvalidR")
+    if s > SECP256K1_N // 2:            # ecdsa.zig:33: malleability rule
+        raise SenderError("InvalidS")
+    raw = [body[it[1]:it[3]] for it in items[:-3]]
+    if typed:
+        if v > 1:
+            raise SenderError("InvalidTransaction")  # y_parity is one bit
+        return b[:1] + _rlp_list(raw), r, s, v
+    if v in (27, 28):
+        recid = v - 27
+    else:
+        v155 = 35 + 2 * chain_id
+        if v not in (v155, v155 + 1):
+            raise SenderError("EIP155_v")
+        recid = v - v155
+    if chain_id != SPEC_TEST_CHAIN_ID:   # signer.zig:87: EIP-155 form whenever the signer's chain is not the spec-test chain
+        raw = raw + [_rlp_uint(chain_id), b"\x80", b"\x80"]
+    return _rlp_list(raw), r, s, recid
+
+
+def get_senders(ctx, encoded_txs, chain_id=1):
+    """TxSigner.get_sender (src/signer/signer.zig:41-79) for every transaction of a block: one K call for the signing
+    hashes, one R call (phant_gpu_ecrecover_batch: recovery and address hashing fused) for the senders.  Returns a list
+    with, per transaction, the 20-byte address or the SenderError the reference would have raised."""
+    out = [None] * len(encoded_txs)
+    parts = []
+    for i, tx in enumerate(encoded_txs):
+        try:
+            parts.append((i,) + _tx_signing_parts(tx, chain_id))
+        except SenderError as e:
+            out[i] = e
+    if not parts:
+        return out
+    hashes = keccak256_batch(ctx, [p[1] for p in parts])
+    n = len(parts)
+    h = np.frombuffer(b"".join(hashes), np.uint8)
+    sig = np.frombuffer(b"".join(p[2].to_bytes(32, "big") + p[3].to_bytes(32, "big") + bytes([p[4]]) for p in parts), np.uint8)
+    addr = np.zeros((n, 20), np.uint8)
+    ok = np.zeros(n, np.uint8)
+    ctx.ecrecover_batch(h, sig, n, None, addr, ok)
+    for j, p in enumerate(parts):
+        out[p[0]] = addr[j].tobytes() if ok[j] else SenderError("RecoveryFailed")
+    return out

@@ -162,6 +162,20 @@ def tx_hash_kat():
                               "cases": [{"encoded": e, "hash": h} for e, h in cases]})
 
 
+# ---------------------------------------------------------------- sender recovery (src/crypto/ecdsa.zig:38-48, src/signer/signer.zig:199-227)
+def ecrecover_kat():
+    src = open(f"{REF}/src/crypto/ecdsa.zig").read()
+    get = lambda name: re.search(name + r' = common\.comptimeHexToBytes\("([0-9a-f]+)"\)', src).group(1)
+    erecover = {"hash": get("hashed_msg"), "sig65": get("signature"), "pubkey65": get("uncompressed_pubkey")}
+    assert len(erecover["sig65"]) == 130 and len(erecover["pubkey65"]) == 130
+    ssrc = open(f"{REF}/src/signer/signer.zig").read()
+    txs = re.findall(r'\.rlp_encoded = "([0-9a-f]+)",\s*\.expected_sender = "([0-9a-f]{40})"', ssrc)
+    assert len(txs) == 2, len(txs)  # legacy post-EIP-155 and EIP-1559, both mainnet
+    dump("ecrecover_kat.json", {"source": "src/crypto/ecdsa.zig:38-48 (geth-generated erecover vector), src/signer/signer.zig:199-227 "
+                                          "(mainnet transactions with known senders, chain id 1)",
+                                "erecover": erecover, "txs": [{"encoded": e, "sender": a, "chain_id": 1} for e, a in txs]})
+
+
 # ---------------------------------------------------------------- fixtures
 def rlp_decode(b, pos=0):
     """-> (item, next_pos); item is bytes or list.  For list items also keep the raw encoding."""
@@ -245,4 +259,5 @@ if __name__ == "__main__":
     mptize_kat()
     evmone_kat()
     tx_hash_kat()
+    ecrecover_kat()
     fixtures()

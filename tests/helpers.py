@@ -197,3 +197,25 @@ def py_mptize(keccak, kv):
     items = [([n for b in k for n in (b >> 4, b & 15)], v) for k, v in kv]
     node = _py_node(keccak, items, 0)
     return keccak(node if node else b"\x80")
+
+
+# ---- a stand-in for phant_b200.gpu.Context that computes with the CPU oracle: lets the HOST logic above the C ABI
+# (flattening, decoding, ownership, error mapping) run in the CPU test suite; the -m gpu tests run the same host code on the device
+class OracleBackedCtx:
+    def __init__(self, o):
+        self.o = o
+
+    def keccak256_batch(self, data, off, n, out):
+        import numpy as np
+        for i in range(n):
+            out[i] = np.frombuffer(self.o.keccak256(data[int(off[i]):int(off[i + 1])].tobytes()), np.uint8)
+
+    def ecrecover_batch(self, hashes32, sigs65, n, pubkeys65, addresses20, ok):
+        import numpy as np
+        for i in range(n):
+            pub = self.o.ecrecover(hashes32[32 * i:32 * i + 32].tobytes(), sigs65[65 * i:65 * i + 65].tobytes())
+            ok[i] = 1 if pub else 0
+            if pubkeys65 is not None:
+                pubkeys65[i] = np.frombuffer(pub or bytes(65), np.uint8)
+            if addresses20 is not None:
+                addresses20[i] = np.frombuffer(self.o.keccak256(pub[1:])[12:] if pub else bytes(20), np.uint8)

@@ -138,6 +138,19 @@ class Oracle:
         self.lib.oracle_logs_bloom(_p(data, u8p), _p(off, u64p), _p(own, u32p), len(items), n_blooms, _p(out, u8p))
         return out[:n_blooms]
 
+    # -- secp256k1 recovery --
+    def ecrecover(self, hash32, sig65):
+        """-> 65-byte public key (0x04 || X || Y) or None when the signature recovers no key"""
+        out = C.create_string_buffer(65)
+        self.lib.oracle_ecrecover.restype = C.c_int
+        rc = self.lib.oracle_ecrecover(bytes(hash32), bytes(sig65), out)
+        return out.raw if rc == 0 else None
+
+    def secp256k1_pubkey(self, priv32):
+        out = C.create_string_buffer(65)
+        assert self.lib.oracle_secp256k1_pubkey(bytes(priv32), out) == 0
+        return out.raw
+
     # -- mptize --
     def mptize(self, kv):
         keys, koff = csr([k for k, _ in kv], np.uint32)
