@@ -62,4 +62,4 @@ def test_random_inputs_vs_oracle(ctx, oracle):
             n_ok += 1
         else:
             assert not pub[i].any() and not addr[i].any()
-    assert 800 < n_ok < 2200
+    assert n_ok == 752  # what the oracle says for this seed: recid 2 / 3 almost never lifts, half of the abscissae are off the curve
