@@ -17,7 +17,7 @@ static Bytes X(const std::string& hex)
     for (size_t i = 0; i + 1 < hex.size(); i += 2) out.push_back((uint8_t)std::stoi(hex.substr(i, 2), nullptr, 16));
     return out;
 }
-static std::string H(const Hash32& h)
+template <class Bytes_> static std::string H(const Bytes_& h)
 {
     static const char* d = "0123456789abcdef";
     std::string s;
@@ -105,6 +105,19 @@ int main()
             for (size_t b = 0; b < all.refs.size(); ++b) all.refs[b] |= part.refs[b];
         }
         expect(H(state::StateDB::rootFromSubtreeRoots(g, all)), big_root, ("sharded StateDB.root world " + std::to_string(world)).c_str());
+    }
+    // ---- sender recovery: the geth-generated vector of src/crypto/ecdsa.zig:38-48, and a signature that recovers nothing ----
+    {
+        const Bytes hm = X("05e0e0ff09b01e5626daac3165b82afa42be29197b82e8a5a8800740ee7519d2");
+        const Bytes sg = X("5a62891eb3e26f3a2344f93a7bad7fe5e670dc45cbdbf0e5bbdba4399238b5e6614caf592f96ee273a2bf018a976e7bf4b63777f9e53ce819d96c5035611400600");
+        const Bytes pk = X("682bade67348db99074fcaaffef29394192e7e227a2bdb49f930c74358060c6a42df70f7ef8aadd94854abe646e047142fad42811e325afbec4753342d630b1e");
+        Hash32 h{}; std::array<uint8_t, 65> s1{}, s0{};
+        std::copy(hm.begin(), hm.end(), h.begin());
+        std::copy(sg.begin(), sg.end(), s1.begin());
+        const auto snd = signer::getSenders(g, {h, h}, {s1, s0}); // s0: r = s = 0
+        const Hash32 want = hasher::keccak256(g, pk);
+        expect(H(Bytes(snd.addresses[0].begin(), snd.addresses[0].end())), H(Bytes(want.begin() + 12, want.end())), "getSenders: erecover vector");
+        expect(std::to_string((int)snd.recovered[0]) + std::to_string((int)snd.recovered[1]), "10", "getSenders: recovered flags");
     }
     // ---- witness: an absent key under the empty root, and a bogus chain ----
     engine_api::Witness w;

@@ -9,6 +9,7 @@
 //   state::StateDB::root                          hook src/blockchain/blockchain.zig:83-85 (missing in the reference)
 //   state::StateDB::subtreeRoots / rootFromSubtreeRoots   the same root sharded over GPUs by top nibble
 //   engine_api::verifyWitness                     hook src/engine_api/execution_payload.zig:177-178 (TODO in the reference)
+//   signer::getSenders                            src/signer/signer.zig:78-79 (erecover + keccak) for a whole block
 //
 // No arithmetic happens here: every hash and every root comes from libphantgpu.so.  Errors from the library
 // surface as phant::GpuError (the Zig binding maps them to error.GpuBackend).
@@ -257,6 +258,27 @@ private:
     };
 };
 } // namespace state
+
+namespace signer {
+// The tail of TxSigner.get_sender (src/signer/signer.zig:78-79) for many transactions at once: sigs65[i] = r || s || recid over
+// the signing hash hashes[i]; addresses[i] is the sender, recovered[i] false where libsecp256k1 would have returned an error.
+// validateSignatureFields and the EIP-155 `v` decoding (signer.zig:41-76) stay with the caller, as in the reference.
+struct Senders {
+    std::vector<Address> addresses;
+    std::vector<uint8_t> recovered;
+};
+inline Senders getSenders(Gpu& g, const std::vector<Hash32>& hashes, const std::vector<std::array<uint8_t, 65>>& sigs65)
+{
+    if (hashes.size() != sigs65.size()) throw GpuError(PHANT_GPU_E_INVALID, "getSenders: one signature per hash");
+    Senders out;
+    out.addresses.resize(hashes.size());
+    out.recovered.resize(hashes.size());
+    if (!hashes.empty())
+        g.check(phant_gpu_ecrecover_batch(g.ctx(), hashes[0].data(), sigs65[0].data(), hashes.size(), nullptr, out.addresses[0].data(),
+                                          out.recovered.data()), "getSenders");
+    return out;
+}
+} // namespace signer
 
 namespace engine_api {
 // execution_payload.zig:125-139: index trie keyed by the 32-byte big-endian index (phant's non-standard keys)

@@ -19,6 +19,7 @@ python tools/kbench.py --which 3 --n 2000000 --iters 5 --variants staged > $OUT/
 for sz in 532 112 32; do python tools/kbench.py --uniform $sz --n 4000000 --iters 5; done > $OUT/kbench_uniform_$TAG.jsonl 2>&1
 tail -2 $OUT/kbench_c3_$TAG.jsonl | cut -c1-220
 step "builders";             python tools/builders_bench.py > $OUT/builders_$TAG.jsonl 2> $OUT/builders_$TAG.err; cut -c1-160 $OUT/builders_$TAG.jsonl
+step "ecrecover";           python tools/ecrecover_bench.py > $OUT/ecrecover_$TAG.json 2> $OUT/ecrecover_$TAG.err; cut -c1-300 $OUT/ecrecover_$TAG.json
 step "ncu launch list (shares only)"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_b_$TAG.log 2>&1

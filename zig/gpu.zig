@@ -97,6 +97,14 @@ pub const Gpu = struct {
             return error.GpuBackend;
     }
 
+    /// The tail of TxSigner.get_sender (src/signer/signer.zig:78-79) for a whole block: sigs65[i] = r || s || recid over
+    /// hashes[i]; ok[i] == 0 where erecover would have failed.
+    pub fn recoverSenders(self: *Gpu, hashes: []const Hash32, sigs65: []const [65]u8, addresses: [][20]u8, ok: []u8) Error!void {
+        std.debug.assert(hashes.len == sigs65.len and hashes.len == addresses.len and hashes.len == ok.len);
+        if (c.phant_gpu_ecrecover_batch(self.ctx, @ptrCast(hashes.ptr), @ptrCast(sigs65.ptr), hashes.len, null, @ptrCast(addresses.ptr), ok.ptr) != 0)
+            return error.GpuBackend;
+    }
+
     /// Receipt.calculateLogsBloom (src/types/receipt.zig:37-48) for all receipts of a block.
     pub fn logsBlooms(self: *Gpu, items: []const u8, item_off: []const u64, bloom_of_item: []const u32, blooms: []types.LogsBloom) Error!void {
         if (c.phant_gpu_logs_bloom(self.ctx, items.ptr, item_off.ptr, bloom_of_item.ptr, bloom_of_item.len, blooms.len, @ptrCast(blooms.ptr)) != 0)
