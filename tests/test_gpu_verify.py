@@ -3,7 +3,6 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from gpu_util import bit
 from helpers import secure_account_items
 from test_oracle_proofs import batch_of, mutations
 

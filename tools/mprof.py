@@ -1,4 +1,4 @@
-import os, sys
+import sys
 import numpy as np
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 from phant_b200 import gpu
