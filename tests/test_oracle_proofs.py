@@ -175,7 +175,6 @@ def test_synthetic_witnesses(oracle, which):
 
 
 def test_ctrie_update_matches_full_rebuild(oracle):
-    from helpers import rlp_list, rlp_str
     depth = 3
     t = oracle.ctrie(depth)
     r0 = t.root()
