@@ -81,10 +81,21 @@ def cpu_arm(sample_proofs, target_cpu_seconds, threads):
         o.verify_proofs(nodes, node_off, first, keys, roots, threads=threads)
     dt = time.perf_counter() - t0
     value = sample_proofs * reps / dt
+    # phant's own path is single-threaded (SURVEY.md 8d asks for both figures): the same walk on ONE core, ~2 s of work
+    one = min(sample_proofs, 16384)
+    first1 = first[:one + 1]
+    t0 = time.perf_counter()
+    o.verify_proofs(nodes, node_off, first1, keys[:32 * one], roots[:32 * one], threads=1)
+    t1core = time.perf_counter() - t0
+    reps1 = max(1, min(50, int(2.0 / max(t1core, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(reps1):
+        o.verify_proofs(nodes, node_off, first1, keys[:32 * one], roots[:32 * one], threads=1)
+    one_core = one * reps1 / (time.perf_counter() - t0)
     o.use_reference_keccak(False)
     what = ("oracle proof walk (phant has no verifier) over the reference's own keccak.c compiled unchanged (oracle/_ref)"
             if kind == "reference" else "oracle C port (oracle/_ref absent)")
-    return {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "one_core": one_core,
             "sample": f"{sample_proofs} proofs of the same workload x {reps} passes, {threads} threads, {dt:.2f} s wall; {what}"}
 
 
