@@ -475,3 +475,30 @@ def get_senders(ctx, encoded_txs, chain_id=1):
     for j, p in enumerate(parts):
         out[p[0]] = addr[j].tobytes() if ok[j] else SenderError("RecoveryFailed")
     return out
+
+
+# ---- the payload handler with its TODO filled in (src/engine_api/execution_payload.zig:125-183) -------------------------------
+def new_payload_v2(ctx, transactions, withdrawals, witness=None, parent_state_root=None, touched_hashed_keys=(), chain_id=1):
+    """What newPayloadV2Handler does before it hands the block to runBlock, as three library calls for the whole payload:
+
+      * ExecutionPayload.toBlock's two tries (:125-158; keys are the 32-byte big-endian index, phant's non-standard choice)
+        built as ONE forest (M);
+      * "reconstruct the proof from the execution witness and verify it" (:177-178): the witness blob decoded and every
+        touched key resolved inside its node set from the parent state root (W);
+      * the senders of all transactions (signer.zig:41-79) in one recovery call (R).
+
+    transactions / withdrawals: encoded items.  Returns a dict; `accept` is False when the witness is undecodable or any
+    touched key is rejected (0) or lacks a node (3) -- the payload must then be refused before execution."""
+    if transactions or withdrawals:
+        tx_root, wd_root = mptize_many(ctx, [[KeyVal(i.to_bytes(32, "big"), v) for i, v in enumerate(items)] for items in (transactions, withdrawals)])
+    else:
+        tx_root = wd_root = EMPTY_MPT_ROOT  # mpt.zig:41: an empty list hashes to the constant
+    out = {"transactions_root": tx_root, "withdrawals_root": wd_root, "witness_status": None, "witness_error": None,
+           "senders": get_senders(ctx, transactions, chain_id), "accept": True}
+    if witness is not None:
+        try:
+            out["witness_status"] = verify_payload_witness(ctx, parent_state_root, witness, list(touched_hashed_keys))
+            out["accept"] = all(s in (1, 2) for s in out["witness_status"])
+        except InvalidWitness as e:
+            out["witness_error"], out["accept"] = str(e), False
+    return out

@@ -210,6 +210,18 @@ class OracleBackedCtx:
         for i in range(n):
             out[i] = np.frombuffer(self.o.keccak256(data[int(off[i]):int(off[i + 1])].tobytes()), np.uint8)
 
+    def mpt_roots(self, keys, key_off, vals, val_off, seg_off, n_tries):
+        out = []
+        for t in range(n_tries):
+            kv = [(keys[int(key_off[i]):int(key_off[i + 1])].tobytes(), vals[int(val_off[i]):int(val_off[i + 1])].tobytes())
+                  for i in range(int(seg_off[t]), int(seg_off[t + 1]))]
+            out.append(self.o.mptize(kv))
+        return out
+
+    def verify_witness(self, n_nodes, nodes, node_off, n_keys, keys32, roots32, n_roots, bitmap, status, val_off, val_len):
+        st = self.o.verify_bag(nodes, node_off, keys32, roots32, threads=1)[0]
+        status[:] = st
+
     def ecrecover_batch(self, hashes32, sigs65, n, pubkeys65, addresses20, ok):
         import numpy as np
         for i in range(n):

@@ -55,3 +55,28 @@ def test_every_truncation_and_byte_flip_in_the_framing_is_refused_or_changes_the
         except host.InvalidWitness:
             continue
         assert got != (h, c, n)  # decodable, but then it is a different witness (the walk will judge its nodes)
+
+
+def test_new_payload_v2_over_an_oracle_backed_context(oracle, golden):
+    """the handler mirror end to end on the CPU (host logic only; tests/test_gpu_host_py.py runs it on the device): roots of
+    the payload's two lists with 32-byte index keys, witness verdicts, senders"""
+    from helpers import OracleBackedCtx, secure_account_items
+    ctx = OracleBackedCtx(oracle)
+    g = golden("fixture_states.json.gz")
+    accounts = max(g["tables"].values(), key=len)[:40]
+    items = secure_account_items(oracle.keccak256, oracle.mptize, accounts)
+    trie = oracle.trie(items)
+    keys = [k for k, _ in items[:10]] + [oracle.keccak256(b"nobody")]
+    nodes = list({nd: 1 for k in keys for nd in trie.prove(k)})
+    txs = [bytes.fromhex(t["encoded"]) for t in golden("ecrecover_kat.json")["txs"]]
+    wds = [host._rlp_list([host._rlp_uint(i), host._rlp_uint(7), host._rlp_str(bytes(20)), host._rlp_uint(1000 + i)]) for i in range(5)]
+    r = host.new_payload_v2(ctx, txs, wds, host.encode_witness([], [], nodes), trie.root(), keys, chain_id=1)
+    assert r["accept"] and r["witness_status"] == [1] * 10 + [2]
+    assert [a.hex() for a in r["senders"]] == [t["sender"] for t in golden("ecrecover_kat.json")["txs"]]
+    assert r["transactions_root"] == oracle.mptize([(i.to_bytes(32, "big"), t) for i, t in enumerate(txs)])
+    assert r["withdrawals_root"] == oracle.mptize([(i.to_bytes(32, "big"), w) for i, w in enumerate(wds)])
+    short = host.new_payload_v2(ctx, txs, wds, host.encode_witness([], [], nodes[1:]), trie.root(), keys)
+    assert not short["accept"] and set(short["witness_status"]) & {0, 3}
+    broken = host.new_payload_v2(ctx, txs, wds, b"\xc1", trie.root(), keys)
+    assert not broken["accept"] and broken["witness_error"]
+    assert host.new_payload_v2(ctx, [], [])["accept"]
