@@ -2,7 +2,8 @@
  *
  * Nothing under oracle/ is part of the product.  Only tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py may load this library, and only as the checker
- * (or as the timed CPU baseline).  The product path (phant_b200/csrc -> libphantgpu.so) never links,
+ * (or as the timed CPU baseline; the development benchmarks under tools/ use it the same way -- input generator, checker,
+ * CPU timing -- never as the thing measured).  The product path (phant_b200/csrc -> libphantgpu.so) never links,
  * loads or calls it and fails loudly when the CUDA library is missing.
  *
  * Parity status:

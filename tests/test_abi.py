@@ -53,7 +53,8 @@ def test_no_silent_cpu_fallback():
 
 def test_product_never_imports_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "phant_b200")):
+    walks = [w for d in ("phant_b200", "host", "include", "zig") for w in os.walk(os.path.join(ROOT, d))]
+    for dirpath, _, files in walks:
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
