@@ -176,6 +176,25 @@ def ecrecover_kat():
                                 "erecover": erecover, "txs": [{"encoded": e, "sender": a, "chain_id": 1} for e, a in txs]})
 
 
+# ---------------------------------------------------------------- RLP encodings (evmone/test/unittests/state_rlp_test.cpp)
+def rlp_kat():
+    """zig-rlp is not in the tree (build.zig.zon:5-8); the vendored evmone suite holds encoder vectors for the same wire
+    format: they pin the host-side RLP helpers that prepare builder inputs (uints, long strings, an account body, a trimmed
+    storage value, a leaf node)."""
+    src = open(f"{REF}/evmone/test/unittests/state_rlp_test.cpp").read()
+    uints = [(int(v, 0), h) for v, h in re.findall(r'rlp::encode\(uint64_t\{(0x[0-9a-f]+|\d+)\}\), "([0-9a-f]+)"_hex', src)]
+    assert len(uints) >= 20, len(uints)
+    longs = [(int(n, 16), h) for n, h in re.findall(r'rlp::encode\(\{buffer\.get\(\), (0x[0-9a-f]+)\}\);\s*EXPECT_EQ\(r\d\.size\(\), [^;]+;\s*EXPECT_EQ\(hex\(\{r\d\.data\(\), 10\}\), "([0-9a-f]+)"\)', src)]
+    assert len(longs) == 4, longs
+    acct = re.search(r'encode_account_with_balance\)\s*\{\s*const auto expected =\s*((?:"[0-9a-f ]+"\s*)+)_hex', src).group(1)
+    acct = "".join(re.findall(r'"([0-9a-f ]+)"', acct)).replace(" ", "")
+    node = re.search(r'const auto path = "([0-9a-f]+)"_hex;\s*const auto value = "([0-9a-f]+)"_hex;.*?EXPECT_EQ\(node, "([0-9a-f]+)"_hex\)', src, re.S).groups()
+    dump("rlp_kat.json", {"source": "evmone/test/unittests/state_rlp_test.cpp:35-151", "uint64": [{"value": v, "rlp": h} for v, h in uints],
+                          "long_strings": [{"len": n, "first10": h} for n, h in longs],
+                          "account_nonce0_balance1_empty": acct, "storage_value_0x01ff": "8201ff",
+                          "leaf_node": {"path": node[0], "value": node[1], "rlp": node[2]}})
+
+
 # ---------------------------------------------------------------- fixtures
 def rlp_decode(b, pos=0):
     """-> (item, next_pos); item is bytes or list.  For list items also keep the raw encoding."""
@@ -260,4 +279,5 @@ if __name__ == "__main__":
     evmone_kat()
     tx_hash_kat()
     ecrecover_kat()
+    rlp_kat()
     fixtures()

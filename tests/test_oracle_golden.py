@@ -198,3 +198,32 @@ def test_oracle_state_root_vs_independent_python(oracle, golden):
                         "storage": st})
         items = secure_account_items(oracle.keccak256, lambda kv: py_mptize(oracle.keccak256, kv), acc)
         assert py_mptize(oracle.keccak256, items) == oracle.state_root(acc), trial
+
+
+def test_rlp_encoder_vectors(oracle, golden):
+    """evmone/test/unittests/state_rlp_test.cpp: the wire format zig-rlp (absent from the tree) must produce; pins the RLP
+    helpers that prepare builder inputs in the host mirror (phant_b200/host.py) and in the tests (tests/helpers.py), and --
+    through a one-account state -- the account body the oracle's and the device's state-root builders emit"""
+    from helpers import rlp_int_be, rlp_list, rlp_str, rlp_uint
+    from phant_b200 import host
+    g = golden("rlp_kat.json")
+    for c in g["uint64"]:
+        v, want = c["value"], c["rlp"]
+        assert host._rlp_uint(v).hex() == want == rlp_uint(v).hex() == rlp_int_be(v.to_bytes(8, "big")).hex(), v
+    for c in g["long_strings"]:
+        for enc in (host._rlp_str, rlp_str):
+            r = enc(bytes(c["len"]))
+            assert len(r) == c["len"] + 1 + (r[0] - 0xb7) and r[:10].hex() == c["first10"], c
+    empty_root = bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421")
+    empty_hash = oracle.keccak256(b"")
+    body = [rlp_uint(0), rlp_uint(1), rlp_str(empty_root), rlp_str(empty_hash)]
+    assert rlp_list(body).hex() == g["account_nonce0_balance1_empty"] == host._rlp_list(body).hex()
+    assert rlp_int_be(bytes.fromhex("%064x" % 0x01ff)).hex() == g["storage_value_0x01ff"]
+    leaf = g["leaf_node"]
+    assert rlp_list([rlp_str(bytes.fromhex(leaf["path"])), rlp_str(bytes.fromhex(leaf["value"]))]).hex() == leaf["rlp"]
+    # the same account body inside the oracle's state root: one account (nonce 0, balance 1, no code, no storage)
+    addr = bytes(19) + b"\x07"
+    acct = {"address": addr.hex(), "nonce": 0, "balance": "%064x" % 1, "code": "", "storage": {}}
+    key = oracle.keccak256(addr)
+    leaf_rlp = rlp_list([rlp_str(b"\x20" + key), rlp_str(bytes.fromhex(g["account_nonce0_balance1_empty"]))])
+    assert oracle.state_root([acct]) == oracle.keccak256(leaf_rlp)
