@@ -260,11 +260,14 @@ def fixtures():
             blocks = []
             for b in valid:
                 txs, wds = list_values(bytes.fromhex(b["rlp"][2:]))
+                header_rlp = rlp_decode(bytes.fromhex(b["rlp"][2:]))[0][0][1]  # raw bytes of the block's first item
                 blocks.append({"tx_values": [x.hex() for x in txs], "wd_values": [x.hex() for x in wds],
+                               "header_rlp": header_rlp.hex(), "hash": b["blockHeader"]["hash"][2:],
+                               "parentHash": b["blockHeader"]["parentHash"][2:],
                                "transactionsTrie": b["blockHeader"]["transactionsTrie"][2:],
                                "withdrawalsRoot": b["blockHeader"]["withdrawalsRoot"][2:]})
                 n_blocks += 1
-            tests.append({"file": rel, "name": name, "pre": intern(norm_accounts(t["pre"])),
+            tests.append({"file": rel, "name": name, "genesis_hash": t["genesisBlockHeader"]["hash"][2:], "pre": intern(norm_accounts(t["pre"])),
                           "pre_root": t["genesisBlockHeader"]["stateRoot"][2:],
                           "post": intern(norm_accounts(t["postState"])), "post_root": post_root, "blocks": blocks})
     print(f"fixtures: {len(tests)} tests, {n_blocks} valid blocks, {len(pool)} distinct account tables")

@@ -104,3 +104,13 @@ def test_device_pointer_mode_and_size(ctx, oracle):
     ctx.set_flags(0)
     st = ctx.stats()
     assert st["keccak_msgs"] >= 2 * n and st["keccak_perms"] >= 2 * n * 4 and st["keccak_ms"] > 0
+
+
+def test_fixture_header_hashes(ctx, golden):
+    """the 87 block headers of the fixtures in one K call: keccak256(rlp(header)) == the header's `hash` field
+    (what src/blockchain/blockchain.zig:135-137 relies on); no oracle in the loop"""
+    g = golden("fixture_states.json.gz")
+    blocks = [b for t in g["tests"] for b in t["blocks"]]
+    data, off = oracle_lib.csr([bytes.fromhex(b["header_rlp"]) for b in blocks], np.uint64)
+    got = gpu_hash(ctx, np.concatenate([data, np.zeros(32, np.uint8)]), off)
+    assert [h.tobytes().hex() for h in got] == [b["hash"] for b in blocks] and len(blocks) == 87

@@ -227,3 +227,18 @@ def test_rlp_encoder_vectors(oracle, golden):
     key = oracle.keccak256(addr)
     leaf_rlp = rlp_list([rlp_str(b"\x20" + key), rlp_str(bytes.fromhex(g["account_nonce0_balance1_empty"]))])
     assert oracle.state_root([acct]) == oracle.keccak256(leaf_rlp)
+
+
+def test_fixture_header_hashes(oracle, golden):
+    """src/blockchain/blockchain.zig:135-137 compares parent_hash with the hash of the previous header: in every fixture,
+    keccak256(rlp(header)) of each valid block equals its `hash` field and the next block's `parentHash` (87 headers)"""
+    g = golden("fixture_states.json.gz")
+    n = 0
+    for t in g["tests"]:
+        prev = t["genesis_hash"]
+        for b in t["blocks"]:
+            assert oracle.keccak256(bytes.fromhex(b["header_rlp"])).hex() == b["hash"]
+            assert b["parentHash"] == prev
+            prev = b["hash"]
+            n += 1
+    assert n == 87
