@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+import oracle_lib
 from gpu_util import random_csr
 
 pytestmark = pytest.mark.gpu
