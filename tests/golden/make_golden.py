@@ -195,6 +195,16 @@ def rlp_kat():
                           "leaf_node": {"path": node[0], "value": node[1], "rlp": node[2]}})
 
 
+# ---------------------------------------------------------------- the sample engine_newPayloadV2 request (src/engine_api/test_req.json)
+def engine_payload_kat():
+    d = json.load(open(f"{REF}/src/engine_api/test_req.json"))
+    assert d["method"] == "engine_newPayloadV2"
+    p = d["params"][0]
+    dump("engine_payload_kat.json", {"source": "src/engine_api/test_req.json (test at src/engine_api/engine_api.zig:87-134)",
+                                     "payload": {k: p[k] for k in ("transactions", "receiptsRoot", "stateRoot", "blockHash", "parentHash", "blockNumber")},
+                                     "withdrawals_present": "withdrawals" in p})
+
+
 # ---------------------------------------------------------------- fixtures
 def rlp_decode(b, pos=0):
     """-> (item, next_pos); item is bytes or list.  For list items also keep the raw encoding."""
@@ -283,4 +293,5 @@ if __name__ == "__main__":
     tx_hash_kat()
     ecrecover_kat()
     rlp_kat()
+    engine_payload_kat()
     fixtures()

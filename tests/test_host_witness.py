@@ -80,3 +80,13 @@ def test_new_payload_v2_over_an_oracle_backed_context(oracle, golden):
     broken = host.new_payload_v2(ctx, txs, wds, b"\xc1", trie.root(), keys)
     assert not broken["accept"] and broken["witness_error"]
     assert host.new_payload_v2(ctx, [], [])["accept"]
+
+
+def test_sample_new_payload_request(oracle, golden):
+    """src/engine_api/engine_api.zig:87-134 feeds src/engine_api/test_req.json (no transactions, no withdrawals) to
+    newPayloadV2Handler: its receiptsRoot is the empty-trie constant, and so are the two roots toBlock builds"""
+    from helpers import OracleBackedCtx
+    p = golden("engine_payload_kat.json")["payload"]
+    assert p["transactions"] == [] and p["receiptsRoot"][2:] == host.EMPTY_MPT_ROOT.hex()
+    r = host.new_payload_v2(OracleBackedCtx(oracle), [], [])
+    assert r["transactions_root"] == r["withdrawals_root"] == host.EMPTY_MPT_ROOT == oracle.mptize([]) and r["accept"] and r["senders"] == []
