@@ -475,7 +475,7 @@ extern "C" int phant_gpu_verify_witness(phant_gpu_ctx* ctx, const phant_gpu_witn
     const uint64_t nk = in->n_keys, nn = in->n_nodes;
     if (nk == 0) return PHANT_GPU_OK;
     if (!in->keys32 || !in->roots32 || (nn && !in->node_off) || (in->n_roots != 1 && in->n_roots != nk)) return PHANT_GPU_E_INVALID;
-    if (nn >= (1ull << 31)) return PHANT_GPU_E_INVALID;
+    if (nn > (1ull << 30)) return PHANT_GPU_E_INVALID; // table capacity (2 x nn rounded up to a power of two) must fit 32 bits
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const bool dev = ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS;
@@ -506,7 +506,7 @@ extern "C" int phant_gpu_verify_witness(phant_gpu_ctx* ctx, const phant_gpu_witn
         d_voff = val_off ? (uint64_t*)ctx->d_voff.ptr : nullptr; d_vlen = val_len ? (uint32_t*)ctx->d_vlen.ptr : nullptr;
     }
     uint32_t capacity = 64;
-    while (capacity < 2 * nn) capacity <<= 1; // load factor <= 0.5
+    while ((uint64_t)capacity < 2 * nn) capacity <<= 1; // load factor <= 0.5; nn <= 2^30 bounds this at 2^31
     if (int rc = ctx->d_digests.reserve(ctx, 32 * nn + 32)) return rc;
     if (int rc = ctx->d_summary.reserve(ctx, 4 * nn + 32)) return rc;
     if (int rc = ctx->d_index.reserve(ctx, 4ull * capacity)) return rc;

@@ -1242,10 +1242,11 @@ __device__ __forceinline__ void push_child(uint32_t& sa, uint32_t& acc, const ui
 // aligned words, absorbs it with the product sponge, and stores the digest at level[p].
 __global__ void __launch_bounds__(FR_WARPS * 32)
 frontier_branch_kernel(const uint8_t* __restrict__ child_level, const uint32_t* __restrict__ parents, const uint32_t* __restrict__ count_ptr,
-                       uint32_t bound, uint8_t* __restrict__ level)
+                       uint32_t bound, uint8_t* __restrict__ level, const uint32_t* __restrict__ refuse)
 {
     extern __shared__ __align__(16) uint8_t fr_smem[];
     const uint32_t slot = (uint32_t)__cvta_generic_to_shared(fr_smem) + threadIdx.x * FR_SLOT;
+    if (*refuse) return; // duplicate leaf positions: the update is refused as a whole
     uint32_t count = *count_ptr;
     if (count > bound) count = bound;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
@@ -1274,15 +1275,14 @@ frontier_branch_kernel(const uint8_t* __restrict__ child_level, const uint32_t* 
 // Values up to FR_SLOT - 48 bytes (the caller checks); one thread per leaf.
 __global__ void __launch_bounds__(FR_WARPS * 32)
 frontier_leaf_kernel(const uint8_t* __restrict__ keys32, const uint8_t* __restrict__ vals, const uint32_t* __restrict__ val_off, uint32_t n,
-                     uint32_t depth, uint8_t* __restrict__ leaf_level, uint32_t* __restrict__ pos_out)
+                     uint32_t depth, uint8_t* __restrict__ leaf_level, const uint32_t* __restrict__ pos_in, const uint32_t* __restrict__ refuse)
 {
     extern __shared__ __align__(16) uint8_t fr_smem[];
     const uint32_t slot = (uint32_t)__cvta_generic_to_shared(fr_smem) + threadIdx.x * FR_SLOT;
+    if (*refuse) return; // duplicate leaf positions: the update is refused as a whole
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint8_t* key = keys32 + 32ull * k;
-        uint32_t pos = 0;
-        for (uint32_t i = 0; i < depth; ++i) pos = pos * 16 + ((i & 1) ? (key[i >> 1] & 15u) : (key[i >> 1] >> 4));
-        pos_out[k] = pos;
+        const uint32_t pos = pos_in[k];
         const uint32_t cnt = 64 - depth, hpn = 1 + cnt / 2;
         const uint32_t vl = val_off[k + 1] - val_off[k];
         const uint8_t* v = vals + val_off[k];
@@ -1315,6 +1315,14 @@ frontier_leaf_kernel(const uint8_t* __restrict__ keys32, const uint8_t* __restri
         o[0] = make_uint4((uint32_t)st[0], (uint32_t)(st[0] >> 32), (uint32_t)st[1], (uint32_t)(st[1] >> 32));
         o[1] = make_uint4((uint32_t)st[2], (uint32_t)(st[2] >> 32), (uint32_t)st[3], (uint32_t)(st[3] >> 32));
     }
+}
+
+// sorted leaf positions: two dirty keys on one leaf position (a repeated key, or keys sharing their first `depth` nibbles)
+// would race on leaf_level[pos]; flag it so that every later kernel of the update leaves the trie untouched
+__global__ void ctrie_dup_check_kernel(const uint32_t* __restrict__ sorted_pos, uint64_t n, uint32_t* __restrict__ flag)
+{
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k + 1 < n; k += (uint64_t)gridDim.x * blockDim.x)
+        if (sorted_pos[k] == sorted_pos[k + 1]) *flag = 1;
 }
 
 // children (sorted, `*count` valid of `bound`) -> parents = children >> 4, the tail padded with the last valid value so
@@ -1437,11 +1445,12 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
     if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) && max_val <= FR_SLOT - 48) {
         // ---- fused frontier path: one launch for the leaves, then per level shift/pad + unique + one hash launch; the only
         // host synchronisation is the final read of the root ----
-        static bool attr = false;
-        if (!attr) {
+        static bool attr[64] = {false}; // function attributes are per device (as launch_staged in keccak_kernels.cu)
+        bool& opted = attr[(ctx->device >= 0 && ctx->device < 64) ? ctx->device : 0];
+        if (!opted) {
             CU(cudaFuncSetAttribute(frontier_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM));
             CU(cudaFuncSetAttribute(frontier_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM));
-            attr = true;
+            opted = true;
         }
         RC(ctx->d_b0.reserve(ctx, 4 * n_dirty * 4 + 256));
         uint32_t* pos = (uint32_t*)ctx->d_b0.ptr;
@@ -1449,17 +1458,21 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
         uint32_t* tmp = cur + n_dirty;
         uint32_t* uniq = tmp + n_dirty;
         RC(ctx->d_b3.reserve(ctx, 64));
-        uint32_t* counts = (uint32_t*)ctx->d_b3.ptr; // counts[0] = valid entries of `cur`
+        uint32_t* counts = (uint32_t*)ctx->d_b3.ptr; // counts[0] = valid entries of `cur`; counts[8] = "refused" flag
+        uint32_t* refuse = counts + 8;
         const unsigned fr_grid = (unsigned)((n_dirty + FR_WARPS * 32 - 1) / (FR_WARPS * 32));
         const unsigned fr_cap = (unsigned)keccak_num_sms(ctx->device) * 3;
-        frontier_leaf_kernel<<<fr_grid < fr_cap ? fr_grid : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(d_keys, d_vals, d_voff, (uint32_t)n_dirty, L, t->level[L], pos);
+        // positions first, sorted, checked for collisions; only then is anything written to the resident levels
+        ctrie_leaf_pos_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(d_keys, n_dirty, L, pos);
         size_t temp = 0;
         CU(cub::DeviceRadixSort::SortKeys(nullptr, temp, (const uint32_t*)pos, cur, (int64_t)n_dirty, 0, 4 * (int)L, s));
         RC(ctx->d_cub.reserve(ctx, temp));
         CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub.ptr, temp, (const uint32_t*)pos, cur, (int64_t)n_dirty, 0, 4 * (int)L, s));
-        const uint32_t nd = (uint32_t)n_dirty;
-        CU(cudaMemcpyAsync(counts, &nd, 4, cudaMemcpyHostToDevice, s));
-        ctx->stats.launches += 2;
+        const uint32_t init[16] = {(uint32_t)n_dirty, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        CU(cudaMemcpyAsync(counts, init, sizeof init, cudaMemcpyHostToDevice, s));
+        ctrie_dup_check_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(cur, n_dirty, refuse);
+        frontier_leaf_kernel<<<fr_grid < fr_cap ? fr_grid : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(d_keys, d_vals, d_voff, (uint32_t)n_dirty, L, t->level[L], pos, refuse);
+        ctx->stats.launches += 4;
         uint64_t bound = n_dirty;
         for (int l = (int)L - 1; l >= 0; --l) {
             shift4_pad_kernel<<<grid1d(ctx->device, bound, 256), 256, 0, s>>>(cur, counts, (uint32_t)bound, tmp);
@@ -1471,15 +1484,17 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
             for (int q = 0; q < l; ++q) level_nodes *= 16;
             if (bound > level_nodes) bound = level_nodes; // a level cannot have more dirty nodes than nodes
             const unsigned g = (unsigned)((bound + FR_WARPS * 32 - 1) / (FR_WARPS * 32));
-            frontier_branch_kernel<<<g < fr_cap ? g : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(t->level[l + 1], uniq, counts, (uint32_t)bound, t->level[l]);
+            frontier_branch_kernel<<<g < fr_cap ? g : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(t->level[l + 1], uniq, counts, (uint32_t)bound, t->level[l], refuse);
             ctx->stats.launches += 3;
             uint32_t* x = cur; cur = uniq; uniq = x;
         }
         CU(cudaGetLastError());
+        uint32_t refused = 0;
         CU(cudaMemcpyAsync(out_root, t->level[0], 32, cudaMemcpyDeviceToHost, s));
-        ctx->stats.d2h_bytes += 32;
+        CU(cudaMemcpyAsync(&refused, refuse, 4, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += 36;
         CU(cudaStreamSynchronize(s));
-        return PHANT_GPU_OK;
+        return refused ? PHANT_GPU_E_INVALID : PHANT_GPU_OK; // refused: the trie is unchanged, out_root = its current root
     }
     // ---- general path (device pointers, or leaf values too large for a staging slot):
     // dirty leaves: encode, hash (batched Keccak), scatter into the leaf level ----
@@ -1492,6 +1507,20 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
     uint64_t* offs = sizes + ((n_dirty + 2) & ~1ull);
     uint8_t* dg = (uint8_t*)(offs + ((n_dirty + 2) & ~1ull)); // 16-byte aligned
     ctrie_leaf_pos_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(d_keys, n_dirty, L, pos);
+    {   // distinct leaf positions, checked before anything is written to the resident levels
+        size_t temp0 = 0;
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, temp0, (const uint32_t*)pos, pa, (int64_t)n_dirty, 0, 4 * (int)L, s));
+        RC(ctx->d_cub.reserve(ctx, temp0));
+        CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub.ptr, temp0, (const uint32_t*)pos, pa, (int64_t)n_dirty, 0, 4 * (int)L, s));
+        RC(ctx->d_b3.reserve(ctx, 64));
+        CU(cudaMemsetAsync(ctx->d_b3.ptr, 0, 64, s));
+        ctrie_dup_check_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(pa, n_dirty, (uint32_t*)ctx->d_b3.ptr);
+        uint32_t refused = 0;
+        CU(cudaMemcpyAsync(&refused, ctx->d_b3.ptr, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        ctx->stats.launches += 2;
+        if (refused) return PHANT_GPU_E_INVALID;
+    }
     ctrie_leaf_size_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(d_vals, d_voff, n_dirty, L, sizes);
     RC(scan_sizes(ctx, sizes, offs, n_dirty));
     uint64_t total = 0;
@@ -1503,12 +1532,7 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
     RC(ctx->hash_csr((const uint8_t*)ctx->d_b1.ptr, offs, n_dirty, total, dg));
     ctrie_scatter_kernel<<<grid1d(ctx->device, n_dirty, 256), 256, 0, s>>>(dg, pos, n_dirty, t->level[L]);
     ctx->stats.launches++;
-    // ---- frontier: unique parents level by level (sort once, then shift + unique) ----
-    size_t temp = 0;
-    CU(cub::DeviceRadixSort::SortKeys(nullptr, temp, (const uint32_t*)pos, pa, (int64_t)n_dirty, 0, 4 * (int)L, s));
-    RC(ctx->d_cub.reserve(ctx, temp));
-    CU(cub::DeviceRadixSort::SortKeys(ctx->d_cub.ptr, temp, (const uint32_t*)pos, pa, (int64_t)n_dirty, 0, 4 * (int)L, s));
-    RC(ctx->d_b3.reserve(ctx, 64));
+    // ---- frontier: unique parents level by level (`pa` = the sorted positions, then shift + unique) ----
     uint64_t cnt = n_dirty;
     uint32_t* cur = pa;
     uint32_t* tmp = pb;

@@ -46,7 +46,9 @@ def tx_hashes(ctx, encoded_txs):
 
 def addresses_from_pubkeys(ctx, pubkeys65):
     """the last step of TxSigner.get_sender (src/signer/signer.zig:78): keccak256(pubkey[1..])[12..] for many
-    recovered public keys at once (the secp256k1 recovery itself stays on the CPU: a different kernel family)"""
+    public keys at once.  For keys that still have to be recovered use get_senders below: phant_gpu_ecrecover_batch fuses
+    the secp256k1 recovery with this hashing step on the device, and get_senders does the `v` decoding and
+    validateSignatureFields (ecdsa.zig:28-36) in front of it exactly as signer.zig:41-76 does."""
     return [h[12:] for h in keccak256_batch(ctx, [bytes(p)[1:] for p in pubkeys65])]
 
 
