@@ -192,6 +192,223 @@ def pin_to_gpu_numa_node(gpu_index):
     return None
 
 
+def _peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)")
+
+
+def _max_over_ranks(x, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(xs, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(xs, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t)
+    return [float(v) for v in t.tolist()]
+
+
+def bench_c3(ctx, gpu, torch, dev, rank, world, steps, barrier):
+    """BASELINE configs[2]: 10M storage-slot proofs, depth 4..12, ONE fixed global batch sharded over the ranks (strong
+    scaling), gathered accept bitmap on every rank (phant_gpu_verify_proofs_sharded)."""
+    n_global = int(os.environ.get("PHANT_BENCH_C3_PROOFS", "10000000"))
+    lo, hi = gpu.shard_range(n_global, rank, world)
+    n = hi - lo
+    n_nodes, n_bytes = ctx.synth_sizes(3, n, first=lo)
+    d_nodes = torch.empty(n_bytes + 64, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(n_nodes + 1, dtype=torch.int64, device=dev)
+    d_first = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_keys = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    d_roots = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    ctx.synth(3, n, d_nodes, d_off, d_first, d_keys, d_roots, first=lo)
+    words = gpu.sharded_bitmap_words(n_global, world)
+    g = [torch.zeros(words, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_status = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def step(k):
+        ctx.verify_proofs_sharded(n, n_global, d_nodes, d_off, d_first, d_keys, d_roots, n, g[k & 1], d_status,
+                                  n_nodes=n_nodes, nodes_bytes=n_bytes)
+
+    for k in range(2):
+        step(k)
+    ctx.comm_fence()
+    barrier()
+    ctx.reset_stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(steps):
+        step(k)
+    ctx.comm_fence()
+    ev1.record()
+    torch.cuda.synchronize()
+    st = ctx.stats()
+    dt = _max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, dev, world)
+    idx = torch.arange(lo, hi, device=dev)
+    ok_local = bool(((d_status == 1) == (idx % 97 != 0)).all().item()) and bool(((d_status == 0) == (idx % 97 == 0)).all().item())
+    bits_ok = True
+    for gb in g:  # the gathered bitmap: bit p set iff p % 97 != 0, for every rank's shard
+        b = gb.view(torch.uint8).cpu().numpy()
+        import numpy as np
+        bits = np.unpackbits(b, bitorder="little")[:n_global] if world == 1 else None
+        if world == 1:
+            bits_ok &= bool((bits == (np.arange(n_global) % 97 != 0)).all())
+        else:
+            per = words // world * 64
+            for r in range(world):
+                rlo, rhi = gpu.shard_range(n_global, r, world)
+                seg = np.unpackbits(b[r * per // 8:(r + 1) * per // 8], bitorder="little")[:rhi - rlo]
+                bits_ok &= bool((seg == (np.arange(rlo, rhi) % 97 != 0)).all())
+    tot_nodes, tot_bytes, tot_perms, k_ms, w_ms = _sum_over_ranks(
+        [n_nodes, n_bytes, st["keccak_perms"] / steps, st["keccak_ms"] / steps, st["walk_ms"] / steps], dev, world)
+    peak, _ = _peaks()
+    algo = tot_bytes + 64 * n_global
+    out = {"workload": f"{n_global} synthetic storage-slot proofs, depth 4..12 (full 532-byte branches above level 5, 83-byte 2-child branches "
+                       "below, 66..70-byte leaves), 1 in 97 corrupted; fixed global batch sharded by proof range",
+           "scaling": "strong", "proofs": n_global, "nodes": int(tot_nodes), "node_bytes": int(tot_bytes), "keccak_f": int(tot_perms),
+           "steps": steps, "ms_per_step": 1e3 * dt / steps, "proofs_per_s": n_global * steps / dt,
+           "kernel_ms_mean_per_rank": {"keccak": k_ms / world, "walk": w_ms / world}, "walk_share": w_ms / max(k_ms + w_ms, 1e-9),
+           "keccak_gperm_s": tot_perms / (k_ms / world * 1e-3) / 1e9 if k_ms else None,
+           "roofline": {"bound": "hbm", "achieved": algo / (dt / steps) / 1e9, "peak": peak * world, "unit": "GB/s",
+                        "frac": algo / (dt / steps) / 1e9 / (peak * world), "algorithmic_bytes": int(algo)},
+           "parity": {"status_pattern_ok": ok_local, "gathered_bitmap_ok": bits_ok}}
+    del d_nodes, d_off, d_first, d_keys, d_roots
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_c4(ctx, gpu, torch, dev, steps):
+    """BASELINE configs[3]: 100k dirty leaves into the resident 16^6-leaf trie; every update comes from pinned host memory
+    through the host-pointer ABI (phant_gpu_trie_update), root read back each time.  Replicas only at N > 1."""
+    import numpy as np
+    depth, n = 6, 100_000
+    ctx.set_flags(0)
+    t0 = time.perf_counter()
+    trie = ctx.trie_open(depth)
+    ctx.synchronize()
+    open_s = time.perf_counter() - t0
+    rng = np.random.default_rng(4)
+    sets = []
+    for _ in range(4):
+        pos = rng.choice(16 ** depth, size=n, replace=False).astype(np.uint32)
+        keys = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        keys[:, 0], keys[:, 1], keys[:, 2] = (pos >> 16) & 0xff, (pos >> 8) & 0xff, pos & 0xff
+        vals = rng.integers(0, 256, n * 78, dtype=np.uint8)
+        voff = (np.arange(n + 1) * 78).astype(np.uint32)
+        pin = [torch.from_numpy(a).pin_memory() for a in (np.ascontiguousarray(keys.reshape(-1)), vals, voff)]
+        sets.append(pin)
+    roots = []
+    for s in sets[:2]:
+        roots.append(trie.update(s[0], s[1], s[2], n))
+    ctx.reset_stats()
+    times = []
+    for i in range(steps):
+        s = sets[i % len(sets)]
+        t0 = time.perf_counter()
+        roots.append(trie.update(s[0], s[1], s[2], n))
+        times.append(time.perf_counter() - t0)
+    st = ctx.stats()
+    # same dirty set applied twice to the same trie state gives the same root (set 0 after sets 0..3 cycle): determinism check
+    trie.close()
+    ms = sorted(1e3 * x for x in times)
+    # SURVEY.md 8d: 100k x (112 + 32) + ~151k dirty branches x (512 read + 32 write) = 96.6 MB; 704k Keccak-f
+    algo = 96.6e6
+    peak, _ = _peaks()
+    return {"workload": "100000 dirty leaves into a resident 16-ary trie of 16^6 leaves (17.9M nodes, 573 MB of hashes), host-pointer update",
+            "steps": steps, "ms_per_update": {"min": ms[0], "median": ms[len(ms) // 2], "max": ms[-1]}, "updates_per_s": 1e3 / ms[len(ms) // 2],
+            "launches_per_update": st["launches"] / steps, "h2d_bytes_per_update": st["h2d_bytes"] // steps, "trie_open_s": open_s,
+            "roofline": {"bound": "hbm", "achieved": algo / (ms[len(ms) // 2] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (ms[len(ms) // 2] * 1e-3) / 1e9 / peak, "note": "latency-bound: 7 dependent levels (SURVEY.md 8d)"},
+            "parity": "tests/test_gpu_trie.py::test_resident_trie_full_size (root == oracle full recompute)", "scaling": "replicas only"}
+
+
+def bench_c5(ctx, gpu, torch, dev, rank, world, steps, barrier):
+    """BASELINE configs[4]: 1000 blocks x 300 tx, deduplicated witness per block, BLOCKS sharded over the ranks; per-block
+    verdict = no rejected proof; one all-reduce over u32 reject_count[1000] (phant_gpu_block_reject_counts)."""
+    import numpy as np
+    from phant_b200 import synth_blocks
+    n_blocks = int(os.environ.get("PHANT_BENCH_C5_BLOCKS", "1000"))
+    per = (n_blocks + world - 1) // world
+    b0, b1 = min(rank * per, n_blocks), min((rank + 1) * per, n_blocks)
+    t0 = time.perf_counter()
+    w = synth_blocks.synth_blocks(ctx, dev, b0, b1 - b0, txs=300)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    n = w["n_proofs"]
+    ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+    status = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+    bitmap = torch.zeros((n + 63) // 64 + 1, dtype=torch.int64, device=dev)
+    counts = torch.zeros(n_blocks, dtype=torch.int32, device=dev)
+
+    def step():
+        if n:
+            ctx.verify_proofs(n, w["nodes"], w["node_off"], w["proof_first"], w["keys32"], w["roots32"], n, bitmap, status, None, None,
+                              n_nodes=w["n_nodes"], nodes_bytes=w["n_bytes"], node_index=w["node_index"])
+        ctx.block_reject_counts(status, w["block_of_proof"], n, n_blocks, counts)
+
+    for _ in range(3):
+        step()
+    ctx.synchronize()
+    barrier()
+    ctx.reset_stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    st = ctx.stats()
+    dt = _max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, dev, world)
+    tot = _sum_over_ranks([n, w["n_nodes"], w["n_bytes"], w["n_refs"], st["keccak_ms"] / steps, st["walk_ms"] / steps], dev, world)
+    bad = np.nonzero(counts.cpu().numpy())[0]
+    expect = np.array([b for b in range(n_blocks) if b % 100 == 37])
+    peak, _ = _peaks()
+    algo = tot[2] + 64 * tot[0] + 8 * tot[3]
+    return {"workload": f"{n_blocks} synthetic blocks x 300 tx (2 account proofs depth 8 + 2 storage proofs depth 6 per tx), deduplicated "
+                        "witness, blocks sharded over the ranks, 1 block in 100 corrupted", "scaling": "strong", "blocks": n_blocks,
+            "proofs": int(tot[0]), "unique_nodes": int(tot[1]), "node_bytes": int(tot[2]), "node_refs": int(tot[3]), "steps": steps,
+            "ms_per_batch": 1e3 * dt / steps, "proofs_per_s": tot[0] * steps / dt, "blocks_per_s": n_blocks * steps / dt,
+            "kernel_ms_mean_per_rank": {"keccak": tot[4] / world, "walk": tot[5] / world},
+            "roofline": {"bound": "hbm", "achieved": algo / (dt / steps) / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": algo / (dt / steps) / 1e9 / (peak * world), "algorithmic_bytes": int(algo)},
+            "parity": {"rejected_blocks": bad.tolist(), "rejected_blocks_ok": bool(len(bad) == len(expect) and (bad == expect).all())},
+            "witness_build_s_on_device": gen_s}
+
+
+def bench_mhs(ctx, gpu, torch, dev):
+    """SURVEY.md 8d "Keccak MH/s line": K alone on uniform 532-byte branch nodes (4 Keccak-f each) and 112-byte leaves (1),
+    reported separately; algorithmic bytes = len + 32 per hash."""
+    out = {}
+    ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+    for size, n in ((532, 2_000_000), (112, 8_000_000)):
+        msgs = torch.randint(0, 256, (n * size + 64,), dtype=torch.uint8, device=dev)
+        off = torch.arange(n + 1, dtype=torch.int64, device=dev) * size
+        dg = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+        ctx.keccak256_batch(msgs, off, n, dg)
+        ctx.synchronize()
+        ctx.reset_stats()
+        reps = 5
+        for _ in range(reps):
+            ctx.keccak256_batch(msgs, off, n, dg)
+        st = ctx.stats()
+        sec = st["keccak_ms"] / reps * 1e-3
+        out[str(size)] = {"mh_s": n / sec / 1e6, "gperm_s": st["keccak_perms"] / reps / sec / 1e9, "gb_s": n * (size + 32) / sec / 1e9, "messages": n}
+        del msgs, off, dg
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -201,12 +418,22 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = pin_to_gpu_numa_node(local_rank)  # pinned staging buffers are then first-touched next to this GPU's PCIe root
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before any barrier: forking nvidia-smi must not sit between a barrier and a timed region
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = gpu.Context(local_rank)
-    from phant_b200 import shard
+    if world > 1:
+        # multi-GPU goes through the C ABI (comm.cu): the id travels over whatever channel the host has -- here torch.distributed
+        idt = torch.zeros(gpu.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(gpu.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init(idt.cpu().numpy().tobytes(), rank, world)
     n = PROOFS_PER_GPU
-    first_index, hi = shard.shard_range(world * n, rank, world)  # contiguous, 64-aligned proof ranges (weak scaling)
+    n_global = world * n
+    first_index, hi = gpu.shard_range(n_global, rank, world)  # contiguous, 64-aligned proof ranges (weak scaling)
     assert hi - first_index == n
 
     # ---- witnesses generated in HBM (setup, untimed) ----
@@ -217,24 +444,22 @@ def run_gpu(args, rank, world, local_rank):
     d_keys = torch.empty(n * 32, dtype=torch.uint8, device=dev)
     d_roots = torch.empty(n * 32, dtype=torch.uint8, device=dev)
     ctx.synth(2, n, d_nodes, d_off, d_first, d_keys, d_roots, depth=DEPTH, first=first_index)
-    words = (n + 63) // 64
-    g_bitmap = torch.zeros(world * words, dtype=torch.int64, device=dev)  # global accept bitmap, my slice is mine
-    my_bitmap = g_bitmap[rank * words:(rank + 1) * words]
+    words = gpu.sharded_bitmap_words(n_global, world)
+    per_words = words // world
+    # two gathered bitmaps used alternately: the walk of step k+2 is the first writer to wait for the gather of step k
+    g_bitmaps = [torch.zeros(words, dtype=torch.int64, device=dev) for _ in range(2)]
     d_status = torch.empty(n, dtype=torch.uint8, device=dev)
 
-    # one side stream shared by the library's kernels, torch's ops and NCCL (torch's default stream has handle 0,
-    # which phant_gpu_set_stream reads as "restore the private stream")
+    # one side stream shared by the library's kernels and torch's ops (torch's default stream has handle 0, which
+    # phant_gpu_set_stream reads as "restore the private stream"); the library's collectives run on its own comm stream
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     ctx.set_stream(side.cuda_stream)
 
-    def step_device():
-        if world > 1:
-            g_bitmap.zero_()
-        ctx.verify_proofs(n, d_nodes, d_off, d_first, d_keys, d_roots, n, my_bitmap, d_status, None, None,
-                          n_nodes=n_nodes, nodes_bytes=n_bytes)
-        if world > 1:
-            dist.all_reduce(g_bitmap, op=dist.ReduceOp.SUM)  # one collective per step; disjoint words: SUM == OR
+    def step_device(k):
+        # hash + walk this rank's shard; at N > 1 ONE all-gather of the accept words on the library's comm stream
+        ctx.verify_proofs_sharded(n, n_global, d_nodes, d_off, d_first, d_keys, d_roots, n, g_bitmaps[k & 1], d_status,
+                                  n_nodes=n_nodes, nodes_bytes=n_bytes)
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,38 +469,37 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- device-resident value ----
     ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
-    for _ in range(args.warmup):
-        step_device()
+    for k in range(args.warmup):
+        step_device(k)
+    ctx.comm_fence()
     ctx.synchronize()
     barrier()
     ctx.reset_stats()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step_device()
-    ev1.record()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev_end = torch.cuda.Event(enable_timing=True)
+    evs[0].record()
+    for k in range(args.steps):
+        step_device(k)
+        evs[k + 1].record()
+    ctx.comm_fence()  # the timed region ends when the last gather has landed
+    ev_end.record()
     torch.cuda.synchronize()
-    dt_local = ev0.elapsed_time(ev1) * 1e-3  # device time of exactly K steps on the launching stream
+    dt_local = evs[0].elapsed_time(ev_end) * 1e-3  # device time of exactly K steps incl. the last collective
+    per_step = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps))
     st = ctx.stats()  # per-kernel device time (CUDA events inside the library, same stream)
     barrier()
-    t_step = torch.tensor([dt_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
-    dt = float(t_step.item())
-    value = world * n * args.steps / dt
+    dt = _max_over_ranks(dt_local, dev, world)
+    value = n_global * args.steps / dt
+    step_max = _max_over_ranks(per_step[-1], dev, world)
 
-    # verdict check (outside the timed region): reject iff global index % 97 == 0
+    # verdict check (outside the timed region): reject iff global index % 97 == 0, on the GATHERED bitmaps of both buffers
     expect = np.where((np.arange(n) + first_index) % 97 == 0, 0, 1)
     status_ok = bool((d_status.cpu().numpy() == expect).all())
-    bits = np.unpackbits(g_bitmap.cpu().numpy().view(np.uint8), bitorder="little")
-    if world > 1:
-        allexp = np.concatenate([np.pad(np.where((np.arange(n) + r * n) % 97 == 0, 0, 1), (0, words * 64 - n)) for r in range(world)])
-    else:
-        allexp = np.pad(expect, (0, words * 64 - n))
-    bitmap_ok = bool((bits == allexp).all())
+    bitmap_ok = True
+    for gb in g_bitmaps:
+        bits = np.unpackbits(gb.cpu().numpy().view(np.uint8), bitorder="little")
+        allexp = np.concatenate([np.pad(np.where((np.arange(n) + r * n) % 97 == 0, 0, 1), (0, per_words * 64 - n)) for r in range(world)])
+        bitmap_ok &= bool((bits == allexp).all())
 
     # ---- end to end through the host-pointer ABI ----
     h_nodes = torch.empty(n_bytes + 64, dtype=torch.uint8, pin_memory=True)
@@ -289,10 +513,8 @@ def run_gpu(args, rank, world, local_rank):
     ctx.set_flags(0)
 
     def step_e2e():
-        ctx.verify_proofs(n, h_nodes, h_off, h_first, h_keys, h_roots, n, h_bitmap, h_status, None, None)
-        if world > 1:
-            my_bitmap.copy_(h_bitmap, non_blocking=True)
-            dist.all_reduce(g_bitmap, op=dist.ReduceOp.SUM)
+        # pinned host witness -> H2D -> hash -> walk -> (N > 1: gather) -> gathered bitmap + statuses back on the host
+        ctx.verify_proofs_sharded(n, n_global, h_nodes, h_off, h_first, h_keys, h_roots, n, h_bitmap, h_status)
 
     e2e_steps = max(3, min(args.steps, 10))
     step_e2e()
@@ -304,21 +526,31 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.synchronize()
     dt_e = time.perf_counter() - t0
     st_e = ctx.stats()
-    t_e = torch.tensor([dt_e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(t_e.item())
+    t_e = _max_over_ranks(dt_e, dev, world)
+    e2e_value = n_global * e2e_steps / t_e
     e2e_ok = bool((h_status.numpy() == expect).all())
+    hb = np.unpackbits(h_bitmap.numpy().view(np.uint8), bitorder="little")
+    e2e_ok &= bool((hb == allexp).all())
+    del h_nodes, h_off, h_first, h_keys, h_roots
+
+    # ---- the other BASELINE.json configs, each with its own device timing and parity flag ----
+    extras = {}
+    if not args.skip_extras:
+        del d_nodes, d_off, d_first, d_keys, d_roots
+        torch.cuda.empty_cache()
+        ex_steps = max(3, min(args.steps, 5))
+        ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+        extras["c3"] = bench_c3(ctx, gpu, torch, dev, rank, world, ex_steps, barrier)
+        extras["c5"] = bench_c5(ctx, gpu, torch, dev, rank, world, ex_steps, barrier)
+        barrier()
+        if rank == 0:
+            extras["keccak_by_size"] = bench_mhs(ctx, gpu, torch, dev)
+            extras["c4"] = bench_c4(ctx, gpu, torch, dev, max(5, min(args.steps, 10)))
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        peak, peak_src = _peaks()
         keccak_ms = st["keccak_ms"] / args.steps
         walk_ms = st["walk_ms"] / args.steps
         achieved = ALGO_BYTES_PER_PROOF * n / (keccak_ms * 1e-3) / 1e9
@@ -338,6 +570,10 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": config(world),
+            "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1], "max_over_ranks": step_max,
+                        "note": "per-step CUDA events on rank 0's launching stream; ms_per_step = whole timed region (incl. the last gather) / K, max over ranks"},
+            "collective": ("one ncclAllGather of the accept words per step, issued by libphantgpu.so (phant_gpu_verify_proofs_sharded) on its own "
+                           "comm stream behind an event; two bitmap buffers alternate") if world > 1 else "none (1 GPU)",
             "keccak_mh_s": world * n_nodes / (keccak_ms * 1e-3) / 1e6, "keccak_gperm_s": world * perm_s / 1e9,
             "kernel_ms": {"keccak": keccak_ms, "walk": walk_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -348,10 +584,14 @@ def run_gpu(args, rank, world, local_rank):
                                  "model": "148 SM x 64 INT lanes/clk x sm_mhz / (24 rounds x 180 ALU instr - 122 per message: digest-only last round)"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e["h2d_bytes"] // e2e_steps,
                     "d2h_bytes_per_step": st_e["d2h_bytes"] // e2e_steps, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * float(t_e.item()) / e2e_steps},
+                    "ms_per_step": 1e3 * t_e / e2e_steps},
             "gpu_launches": int(st["launches"]), "clocks": clocks, "host_numa_pin": numa,
             "parity": {"status_ok": status_ok, "bitmap_ok": bitmap_ok, "e2e_ok": e2e_ok},
         }
+        if "keccak_by_size" in extras:
+            line["keccak_mh_s_532"] = extras["keccak_by_size"]["532"]["mh_s"]
+            line["keccak_mh_s_112"] = extras["keccak_by_size"]["112"]["mh_s"]
+        line.update(extras)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_arm(131072, target_cpu_seconds=20.0, threads=host_threads())
         print(json.dumps(line), flush=True)
@@ -370,6 +610,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="phant_b200", choices=["phant_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-extras", action="store_true", help="only the contract workload (C2): no c3 / c4 / c5 / MH-by-size keys")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

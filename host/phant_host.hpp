@@ -215,6 +215,22 @@ public:
         return out;
     }
 
+    // the same, with the exchange behind the ABI (phant_gpu_state_root_sharded: subtree roots here, ONE all-gather over the
+    // communicator of phant_gpu_comm_init / _init_local, root branch hashed on every rank); call it on every rank
+    Hash32 rootSharded(Gpu& g, int rank, int world) const
+    {
+        std::vector<Bytes> addrs;
+        for (const auto& [a, acc] : db) addrs.emplace_back(a.begin(), a.end());
+        const std::vector<Hash32> h = hasher::keccak256_batch(g, addrs);
+        size_t i = 0;
+        std::map<Address, int> slot;
+        for (const auto& [a, acc] : db) slot[a] = h[i++][0] >> 4;
+        Flat f(db, [&](const Address& a) { return phant_gpu_nibble_owner(slot[a], world) == rank; });
+        Hash32 r;
+        g.check(phant_gpu_state_root_sharded(g.ctx(), &f.t, r.data()), "StateDB.rootSharded");
+        return r;
+    }
+
     // after the all-gather (slots are disjoint between ranks, so summing / or-ing the shares is the gather): the root
     // branch rlp([ref_0 .. ref_15, ""]) hashed with one K call.  Needs >= 2 populated slots -- otherwise the root is not
     // a branch and the one rank that owns the populated slot holds every account: it calls root() on its share.

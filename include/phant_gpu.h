@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PHANT_GPU_ABI_VERSION 1
+#define PHANT_GPU_ABI_VERSION 2 /* 2: multi-GPU entry points (phant_gpu_comm_*, *_sharded), U kind 1 */
 
 enum {
     PHANT_GPU_OK = 0,
@@ -38,7 +38,7 @@ enum {
     PHANT_GPU_E_NO_DEVICE = -2, /* no CUDA device / driver */
     PHANT_GPU_E_OOM = -3,       /* device or pinned-host allocation failed */
     PHANT_GPU_E_CUDA = -4,      /* any other CUDA runtime error (phant_gpu_last_error has the text) */
-    PHANT_GPU_E_COMM = -5,      /* collective failed (multi-GPU host layer) */
+    PHANT_GPU_E_COMM = -5,      /* NCCL not loadable / communicator missing / a collective failed (phant_gpu_last_error) */
     PHANT_GPU_E_MALFORMED = -6  /* malformed RLP in a *builder* input (never used for proofs) */
 };
 
@@ -206,6 +206,42 @@ int phant_gpu_trie_root(phant_gpu_trie* trie, uint8_t out_root[32]);
 int phant_gpu_trie_update(phant_gpu_trie* trie, const uint8_t* keys32, const uint8_t* leaf_vals,
                           const uint32_t* val_off, uint64_t n_dirty, uint8_t out_root[32]);
 void phant_gpu_trie_close(phant_gpu_trie* trie);
+
+/* ---- multi-GPU: proofs shard by contiguous index range, one context per GPU, the only exchange is the
+ * accept bitmap.  The reference runs block processing on httpz worker threads (src/main.zig:143-149): either one process
+ * with one context + host thread per GPU (phant_gpu_comm_init_local), or one process per GPU (phant_gpu_comm_init with an
+ * id from rank 0, carried by whatever channel the host has).  NCCL is loaded at run time (libnccl.so.2, override with
+ * PHANT_GPU_NCCL_LIB); single-GPU users never touch it.  Failures return PHANT_GPU_E_COMM. ---- */
+#define PHANT_GPU_COMM_ID_BYTES 128
+int phant_gpu_comm_get_unique_id(uint8_t id[PHANT_GPU_COMM_ID_BYTES]);                            /* rank 0, then distribute */
+int phant_gpu_comm_init(phant_gpu_ctx* ctx, const uint8_t id[PHANT_GPU_COMM_ID_BYTES], int rank, int world); /* collective */
+int phant_gpu_comm_init_local(phant_gpu_ctx** ctxs, int n); /* one process: n contexts on n devices, rank i = ctxs[i]; afterwards
+                                                               drive each context from its own host thread */
+int phant_gpu_comm_info(const phant_gpu_ctx* ctx, int* rank, int* world, int* nccl_version);
+int phant_gpu_comm_fence(phant_gpu_ctx* ctx);   /* the context's stream waits (on the device) for every collective issued so far */
+int phant_gpu_comm_destroy(phant_gpu_ctx* ctx); /* also done by phant_gpu_destroy */
+/* Rank r of `world` owns proofs [lo, hi): contiguous, every boundary but the last a multiple of 64 so that bitmap words
+ * are disjoint.  A gathered bitmap has phant_gpu_sharded_bitmap_words(n, world) words (>= ceil(n/64): equal slices). */
+int phant_gpu_shard_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi);
+uint64_t phant_gpu_sharded_bitmap_words(uint64_t n, int world);
+/* V across GPUs: `local` holds THIS rank's shard of a batch of n_global proofs (local->n_proofs == hi - lo); on return
+ * global_bitmap holds every rank's accept bits (bit p = proof p of the global batch); status / val_* cover the local shard.
+ * Host pointers: synchronous.  Device pointers: Keccak + walk are enqueued on the context's stream and ONE ncclAllGather on
+ * the context's comm stream behind an event -- the next call's Keccak overlaps it; the walk that next writes the same
+ * global_bitmap buffer waits for it on the device (alternate two buffers and nothing ever waits); phant_gpu_comm_fence or
+ * phant_gpu_synchronize before reading. */
+int phant_gpu_verify_proofs_sharded(phant_gpu_ctx* ctx, const phant_gpu_proof_batch* local, uint64_t n_global,
+                                    uint64_t* global_bitmap, uint8_t* status, uint64_t* val_off, uint32_t* val_len);
+/* Per-block verdicts when BLOCKS are sharded (BASELINE.json "1000 blocks x 300 tx"): counts[b] = proofs of block b that
+ * were not accepted (status 0 or 3), summed over ranks with one all-reduce; block b is valid iff counts[b] == 0. */
+int phant_gpu_block_reject_counts(phant_gpu_ctx* ctx, const uint8_t* status, const uint32_t* block_of_proof, uint64_t n_proofs,
+                                  uint64_t n_blocks, uint32_t* counts);
+/* S across GPUs: rank r passes the accounts whose top nibble of keccak(address) it owns (phant_gpu_nibble_owner: contiguous
+ * slot ranges); subtree roots are built locally, ONE all-gather of 528 bytes per rank follows and every rank hashes the
+ * root branch itself.  Fewer than two populated slots overall: the one rank holding accounts computes the plain root and
+ * broadcasts it.  Host pointers only. */
+int phant_gpu_nibble_owner(int nibble, int world);
+int phant_gpu_state_root_sharded(phant_gpu_ctx* ctx, const phant_gpu_accounts* mine, uint8_t out_root[32]);
 
 /* Synthetic witnesses generated on the device (byte-identical to oracle/synth.c).
  * All pointers are DEVICE pointers regardless of the context flags.  which: 2 = account proofs of

@@ -4,7 +4,6 @@
 #include "common.cuh"
 #include "ctx.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <stdio.h>
@@ -131,6 +130,7 @@ extern "C" void phant_gpu_destroy(phant_gpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    phant_gpu_comm_destroy(ctx);
     for (DevBuf* b : ctx->all_bufs()) b->release();
     for (EventPair& p : ctx->pairs)
         if (p.a) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -160,6 +160,7 @@ extern "C" int phant_gpu_synchronize(phant_gpu_ctx* ctx)
     if (!ctx) return PHANT_GPU_E_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) CU(cudaStreamSynchronize(ctx->comm_stream));
     return PHANT_GPU_OK;
 }
 extern "C" int phant_gpu_get_stats(phant_gpu_ctx* ctx, phant_gpu_stats* out)
@@ -201,25 +202,21 @@ int phant_gpu_ctx::hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64
     if (flags & PHANT_GPU_FLAG_KECCAK_WARP) variant = KECCAK_WARP;
     if (variant == KECCAK_STAGED && ((uintptr_t)d_msgs & 15)) variant = KECCAK_DIRECT; // bulk copies need 16-byte alignment
 
-    // classify (always: it also counts the permutations for the stats) and, optionally, regroup
+    // classify (always: it also counts the permutations for the stats) and, optionally, regroup -- two launches of our
+    // own (keccak_kernels.cu "regrouping"), no library sort on the hot path
     if (int rc = d_perms.reserve(ctx, 64)) return rc;
-    if (!perms_init) { CU(cudaMemsetAsync(d_perms.ptr, 0, 8, stream)); perms_init = true; }
-    if (int rc = d_cls.reserve(ctx, n)) return rc;
-    if (int rc = d_idx.reserve(ctx, 4 * n)) return rc;
-    CU(launch_keccak_classify(stream, device, d_off, n, (uint8_t*)d_cls.ptr, (uint32_t*)d_idx.ptr, (unsigned long long*)d_perms.ptr));
+    if (!perms_init) { CU(cudaMemsetAsync(d_perms.ptr, 0, 64, stream)); perms_init = true; } // [0] permutations, [1] block ticket
+    if (int rc = d_idx.reserve(ctx, keccak_regroup_scratch_bytes(device, n))) return rc;
+    CU(launch_keccak_classify(stream, device, d_off, n, (uint32_t*)d_idx.ptr, (uint32_t*)((unsigned long long*)d_perms.ptr + 1),
+                              (unsigned long long*)d_perms.ptr));
     stats.launches++;
     perms_pending = true;
     const uint32_t* order = nullptr;
     const bool regroup = !(flags & PHANT_GPU_FLAG_NO_BINNING) && variant != KECCAK_WARP && n >= 4096;
     if (regroup) {
-        if (int rc = d_cls2.reserve(ctx, n)) return rc;
         if (int rc = d_order.reserve(ctx, 4 * n)) return rc;
-        size_t temp = 0;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint8_t*)d_cls.ptr, (uint8_t*)d_cls2.ptr, (const uint32_t*)d_idx.ptr,
-                                           (uint32_t*)d_order.ptr, (int64_t)n, 0, 4, stream));
-        if (int rc = d_cub.reserve(ctx, temp)) return rc;
-        CU(cub::DeviceRadixSort::SortPairs(d_cub.ptr, temp, (const uint8_t*)d_cls.ptr, (uint8_t*)d_cls2.ptr, (const uint32_t*)d_idx.ptr,
-                                           (uint32_t*)d_order.ptr, (int64_t)n, 0, 4, stream));
+        CU(launch_keccak_regroup(stream, device, d_off, n, (const uint32_t*)d_idx.ptr, (uint32_t*)d_order.ptr));
+        stats.launches++;
         order = (const uint32_t*)d_order.ptr;
     }
     time_begin(0);
@@ -366,6 +363,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
         if (int rc = ctx->d_summary.reserve(ctx, 4 * n_nodes + 32)) return rc;
         if (int rc = ctx->hash_csr(in->nodes, in->node_off, n_nodes, total, (uint8_t*)ctx->d_digests.ptr, (uint32_t*)ctx->d_summary.ptr)) return rc;
+        if (int rc = ctx->wait_walk_fence()) return rc; // sharded call: the previous gather of this bitmap buffer (comm.cu)
         if (accept_bitmap) CU(cudaMemsetAsync(accept_bitmap, 0, bm_bytes, ctx->stream));
         ctx->time_begin(1);
         CU(launch_walk(ctx->stream, ctx->device, np, in->nodes, in->node_off, in->node_index, in->proof_first, in->keys32, in->roots32, in->n_roots,

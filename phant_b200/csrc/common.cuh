@@ -12,8 +12,12 @@ int keccak_num_sms(int device);
 cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, const uint8_t* msgs, const uint64_t* off,
                           const uint32_t* order, uint64_t n, uint8_t* out, uint32_t* summary /*nullable*/,
                           const uint64_t* len = nullptr /*nullable: message m = msgs[off[m] .. off[m] + len[m])*/);
-cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* off, uint64_t n, uint8_t* cls, uint32_t* idx,
+// regrouping by permutation count (stable 16-bucket counting sort, two launches): classify fills hist[blocks][16], counts the
+// permutations and leaves global start positions in hist; regroup writes `order`
+uint64_t keccak_regroup_scratch_bytes(int device, uint64_t n);
+cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* off, uint64_t n, uint32_t* hist, uint32_t* ticket,
                                    unsigned long long* perms);
+cudaError_t launch_keccak_regroup(cudaStream_t s, int device, const uint64_t* off, uint64_t n, const uint32_t* start, uint32_t* order);
 
 // walk_kernel.cu
 cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,

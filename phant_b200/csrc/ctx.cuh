@@ -38,12 +38,12 @@ struct phant_gpu_ctx {
     DevBuf st_in, st_hash, st_seg, st_tmp, st_sort, st_acc;               // state-root staging
     bool perms_init = false, perms_pending = false;
 
-    std::array<DevBuf*, 39> all_bufs()
+    std::array<DevBuf*, 41> all_bufs()
     {
         return {&d_msgs, &d_off, &d_out, &d_first, &d_keys, &d_roots, &d_digests, &d_bitmap, &d_status, &d_voff, &d_vlen,
                 &d_cls, &d_cls2, &d_idx, &d_order, &d_cub, &d_perms, &d_tmp_a, &d_tmp_b, &d_scan_a, &d_scan_b,
                 &d_b0, &d_b1, &d_b2, &d_b3, &d_b4, &d_b5, &d_b6, &d_b7, &d_b8, &d_b9,
-                &st_in, &st_hash, &st_seg, &st_tmp, &st_sort, &st_acc, &d_summary, &d_index};
+                &st_in, &st_hash, &st_seg, &st_tmp, &st_sort, &st_acc, &d_summary, &d_index, &d_comm, &d_rej};
     }
 
     // device timing of the dominant kernels: event pairs recorded on `stream`, resolved lazily
@@ -52,6 +52,23 @@ struct phant_gpu_ctx {
     // host-pointer pipeline: H2D on copy_stream chunk by chunk, kernels on `stream` behind an event per chunk
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
+    // multi-GPU (comm.cu): one NCCL communicator per context, collectives on their own stream so that the next batch's
+    // Keccak launch never waits for a peer; `fence_events` remembers, per destination buffer, the collective that still
+    // reads / writes it (the walk that next writes that buffer waits for exactly that one)
+    void* comm = nullptr;          // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_compute = nullptr;
+    struct Fence { const void* buf; cudaEvent_t ev; };
+    std::vector<Fence> fence_events;
+    const void* walk_fence_buf = nullptr; // set by the sharded entry point: buffer the next walk launch is about to write
+    DevBuf d_comm, d_rej;
+    void* h_comm = nullptr;        // small pinned staging area (subtree roots, counters)
+    // peer-memory path (comm.cu): symmetric buffers mapped from every rank of the node
+    struct Peer;
+    Peer* peer = nullptr;
+    int wait_walk_fence();
+
     void time_begin(int which);
     void time_end();
     void resolve_times();

@@ -258,21 +258,116 @@ keccak256_warp_kernel(const uint8_t* __restrict__ msgs, const uint64_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// regrouping by permutation count
+// regrouping by permutation count: a stable 16-bucket counting sort in two launches of our own
 // ------------------------------------------------------------------------------------------------
-__global__ void keccak_class_kernel(const uint64_t* __restrict__ off, uint64_t n, uint8_t* __restrict__ cls,
-                                    uint32_t* __restrict__ idx, unsigned long long* __restrict__ perms)
+// Lanes of a warp run in lockstep, so a warp costs max(permutations) over its 32 messages: `order` lists the message
+// indices class by class (heaviest first; class = 15 - min(15, rate blocks)), each class in ascending index order.
+//   launch 1  keccak_class_kernel: block b histograms its contiguous chunk of messages (hist[b][16]) and adds the
+//             chunk's permutation count to the statistics; the LAST block to finish turns the matrix into global start
+//             positions in place (class-major exclusive scan: start[b][c] = sum of classes < c + sum over blocks < b);
+//   launch 2  keccak_regroup_kernel: block b walks the same chunk tile by tile and writes each index at
+//             start[b][c] + (messages of class c seen so far in the chunk): ranks by warp match + a per-tile warp table.
+// No library sort, no temporary storage beyond 64 bytes per block, deterministic output.
+constexpr int CLS_THREADS = 256, CLS_WARPS = CLS_THREADS / 32;
+
+__device__ __forceinline__ uint32_t keccak_class_of(uint64_t len)
 {
+    const uint64_t nb = len / KECCAK_RATE + 1; // permutations of this message
+    return (uint32_t)(15 - (nb > 16 ? 15 : nb - 1));
+}
+
+__global__ void __launch_bounds__(CLS_THREADS)
+keccak_class_kernel(const uint64_t* __restrict__ off, uint64_t n, uint64_t chunk, uint32_t* __restrict__ hist /* gridDim.x * 16 */,
+                    uint32_t* __restrict__ ticket, unsigned long long* __restrict__ perms)
+{
+    __shared__ uint32_t h[16];
+    __shared__ uint32_t cls_total[16];
+    __shared__ bool last;
+    if (threadIdx.x < 16) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
     unsigned long long local = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t nb = (off[i + 1] - off[i]) / KECCAK_RATE + 1; // permutations of this message
-        cls[i] = (uint8_t)(15 - (nb > 16 ? 15 : nb - 1));            // heavy classes first
-        idx[i] = (uint32_t)i;
-        local += nb;
+    for (uint64_t i0 = lo; i0 < hi; i0 += CLS_THREADS) { // whole warps stay converged: the tail is handled by `valid`
+        const uint64_t i = i0 + threadIdx.x;
+        const bool valid = i < hi;
+        uint32_t c = 16;
+        if (valid) {
+            const uint64_t len = off[i + 1] - off[i];
+            c = keccak_class_of(len);
+            local += len / KECCAK_RATE + 1;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        if (valid && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&h[c], __popc(peers));
     }
-    // one atomic per warp
     for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(perms, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(perms, local); // one atomic per warp
+    __syncthreads();
+    if (threadIdx.x < 16) hist[16 * blockIdx.x + threadIdx.x] = h[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // ---- the last block: hist[b][c] -> start[b][c], class-major ----
+    const uint32_t nb = gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t c = warp; c < 16; c += CLS_WARPS) { // totals per class
+        uint32_t t = 0;
+        for (uint32_t b = lane; b < nb; b += 32) t += __ldcg(&hist[16 * b + c]);
+        for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) cls_total[c] = t;
+    }
+    __syncthreads();
+    for (uint32_t c = warp; c < 16; c += CLS_WARPS) {
+        uint32_t carry = 0;
+        for (uint32_t k = 0; k < c; ++k) carry += cls_total[k];
+        for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
+            const uint32_t b = b0 + lane;
+            const uint32_t v = b < nb ? __ldcg(&hist[16 * b + c]) : 0;
+            uint32_t incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += up;
+            }
+            if (b < nb) hist[16 * b + c] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0; // ready for the next call on this stream
+}
+
+__global__ void __launch_bounds__(CLS_THREADS)
+keccak_regroup_kernel(const uint64_t* __restrict__ off, uint64_t n, uint64_t chunk, const uint32_t* __restrict__ start /* gridDim.x * 16 */,
+                      uint32_t* __restrict__ order)
+{
+    __shared__ uint32_t base[16];
+    __shared__ uint32_t wcnt[CLS_WARPS][16];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 16) base[threadIdx.x] = start[16 * blockIdx.x + threadIdx.x];
+    const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    for (uint64_t i0 = lo; i0 < hi; i0 += CLS_THREADS) {
+        if (threadIdx.x < CLS_WARPS * 16) (&wcnt[0][0])[threadIdx.x] = 0;
+        __syncthreads(); // also orders the previous tile's reads of base[] / wcnt[] before they change
+        const uint64_t i = i0 + threadIdx.x;
+        const bool valid = i < hi;
+        const uint32_t c = valid ? keccak_class_of(off[i + 1] - off[i]) : 16;
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) wcnt[warp][c] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            uint32_t pos = base[c] + rank;
+            for (uint32_t w = 0; w < warp; ++w) pos += wcnt[w][c];
+            order[pos] = (uint32_t)i;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < CLS_WARPS; ++w) t += wcnt[w][threadIdx.x];
+            base[threadIdx.x] += t;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,14 +453,34 @@ cudaError_t launch_keccak(cudaStream_t s, int device, KeccakVariant variant, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* off, uint64_t n, uint8_t* cls, uint32_t* idx,
+// blocks * chunk >= n, chunk a multiple of the tile, blocks <= 8 per SM (the scan of the last block is O(16 * blocks))
+static void class_geometry(int device, uint64_t n, uint64_t& blocks, uint64_t& chunk)
+{
+    const uint64_t cap = (uint64_t)keccak_num_sms(device) * 8;
+    chunk = ((n + cap - 1) / cap + CLS_THREADS - 1) / CLS_THREADS * CLS_THREADS;
+    blocks = (n + chunk - 1) / chunk;
+}
+uint64_t keccak_regroup_scratch_bytes(int device, uint64_t n)
+{
+    uint64_t blocks, chunk;
+    class_geometry(device, n ? n : 1, blocks, chunk);
+    return 64 * blocks;
+}
+cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* off, uint64_t n, uint32_t* hist, uint32_t* ticket,
                                    unsigned long long* perms)
 {
     if (n == 0) return cudaSuccess;
-    uint64_t blocks = (n + 255) / 256;
-    const uint64_t cap = (uint64_t)keccak_num_sms(device) * 8;
-    if (blocks > cap) blocks = cap;
-    keccak_class_kernel<<<(unsigned)blocks, 256, 0, s>>>(off, n, cls, idx, perms);
+    uint64_t blocks, chunk;
+    class_geometry(device, n, blocks, chunk);
+    keccak_class_kernel<<<(unsigned)blocks, CLS_THREADS, 0, s>>>(off, n, chunk, hist, ticket, perms);
+    return cudaGetLastError();
+}
+cudaError_t launch_keccak_regroup(cudaStream_t s, int device, const uint64_t* off, uint64_t n, const uint32_t* start, uint32_t* order)
+{
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks, chunk;
+    class_geometry(device, n, blocks, chunk);
+    keccak_regroup_kernel<<<(unsigned)blocks, CLS_THREADS, 0, s>>>(off, n, chunk, start, order);
     return cudaGetLastError();
 }
 

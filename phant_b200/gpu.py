@@ -58,7 +58,11 @@ EXPORTS = [
     "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_ecrecover_batch", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
+    "phant_gpu_comm_get_unique_id", "phant_gpu_comm_init", "phant_gpu_comm_init_local", "phant_gpu_comm_info", "phant_gpu_comm_fence",
+    "phant_gpu_comm_destroy", "phant_gpu_shard_range", "phant_gpu_sharded_bitmap_words", "phant_gpu_verify_proofs_sharded",
+    "phant_gpu_block_reject_counts", "phant_gpu_nibble_owner", "phant_gpu_state_root_sharded",
 ]
+COMM_ID_BYTES = 128
 
 _LIB = None
 
@@ -101,6 +105,19 @@ def _lib():
     L.phant_gpu_trie_close.restype = None
     L.phant_gpu_synth_sizes.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u64p, u64p]
     L.phant_gpu_synth.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, vp, vp, vp, vp, vp]
+    L.phant_gpu_comm_get_unique_id.argtypes = [vp]
+    L.phant_gpu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.phant_gpu_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
+    L.phant_gpu_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.phant_gpu_comm_fence.argtypes = [vp]
+    L.phant_gpu_comm_destroy.argtypes = [vp]
+    L.phant_gpu_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+    L.phant_gpu_sharded_bitmap_words.argtypes = [C.c_uint64, C.c_int]
+    L.phant_gpu_sharded_bitmap_words.restype = C.c_uint64
+    L.phant_gpu_verify_proofs_sharded.argtypes = [vp, C.POINTER(ProofBatch), C.c_uint64, vp, vp, vp, vp]
+    L.phant_gpu_block_reject_counts.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp]
+    L.phant_gpu_nibble_owner.argtypes = [C.c_int, C.c_int]
+    L.phant_gpu_state_root_sharded.argtypes = [vp, C.POINTER(Accounts), vp]
     _LIB = L
     return L
 
@@ -224,6 +241,41 @@ class Context:
     def trie_open(self, depth, seed=0x5048414E54, kind=0):
         return ResidentTrie(self, depth, seed, kind)
 
+    # multi-GPU (comm.cu)
+    def comm_init(self, unique_id, rank, world):
+        """collective: every rank passes the id rank 0 got from comm_unique_id()"""
+        buf = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        self._chk(_lib().phant_gpu_comm_init(self._h, _ptr(buf), rank, world), "comm_init")
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._chk(_lib().phant_gpu_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)), "comm_info")
+        return r.value, w.value, v.value
+
+    def comm_fence(self):
+        self._chk(_lib().phant_gpu_comm_fence(self._h), "comm_fence")
+
+    def comm_destroy(self):
+        self._chk(_lib().phant_gpu_comm_destroy(self._h), "comm_destroy")
+
+    def verify_proofs_sharded(self, n_local, n_global, nodes, node_off, proof_first, keys32, roots32, n_roots, global_bitmap, status=None,
+                              val_off=None, val_len=None, n_nodes=0, nodes_bytes=0, node_index=None):
+        b = ProofBatch(n_local, _ptr(nodes), _ptr(node_off), _ptr(proof_first), _ptr(keys32), _ptr(roots32), n_roots,
+                       n_nodes, nodes_bytes, _ptr(node_index))
+        self._chk(_lib().phant_gpu_verify_proofs_sharded(self._h, C.byref(b), n_global, _ptr(global_bitmap), _ptr(status), _ptr(val_off),
+                                                         _ptr(val_len)), "verify_proofs_sharded")
+
+    def block_reject_counts(self, status, block_of_proof, n_proofs, n_blocks, counts):
+        self._chk(_lib().phant_gpu_block_reject_counts(self._h, _ptr(status), _ptr(block_of_proof), n_proofs, n_blocks, _ptr(counts)),
+                  "block_reject_counts")
+
+    def state_root_sharded(self, n, addr20, nonce, balance32, code, code_off, slot_keys32, slot_vals32, slot_off):
+        a = Accounts(n, _ptr(addr20), _ptr(nonce), _ptr(balance32), _ptr(code), _ptr(code_off), _ptr(slot_keys32),
+                     _ptr(slot_vals32), _ptr(slot_off))
+        out = np.zeros(32, np.uint8)
+        self._chk(_lib().phant_gpu_state_root_sharded(self._h, C.byref(a), _ptr(out)), "state_root_sharded")
+        return out.tobytes()
+
     # synthetic (device pointers)
     def synth_sizes(self, which, n, depth=8, first=0, seed=0x5048414E54):
         a, b = C.c_uint64(), C.c_uint64()
@@ -264,6 +316,38 @@ class ResidentTrie:
             self.ctx._tries.remove(self)
 
     __del__ = close
+
+
+def comm_unique_id():
+    buf = np.zeros(COMM_ID_BYTES, np.uint8)
+    rc = _lib().phant_gpu_comm_get_unique_id(_ptr(buf))
+    if rc != 0:
+        raise PhantGpuError(rc, "comm_get_unique_id", "(libnccl.so.2 not loadable? PHANT_GPU_NCCL_LIB overrides the name)")
+    return buf.tobytes()
+
+
+def comm_init_local(contexts):
+    """one process, one context per device: rank i = contexts[i]; drive each from its own thread afterwards"""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = _lib().phant_gpu_comm_init_local(arr, len(contexts))
+    if rc != 0:
+        raise PhantGpuError(rc, "comm_init_local", _lib().phant_gpu_last_error(contexts[0]._h).decode())
+
+
+def shard_range(n, rank, world):
+    lo, hi = C.c_uint64(), C.c_uint64()
+    rc = _lib().phant_gpu_shard_range(n, rank, world, C.byref(lo), C.byref(hi))
+    if rc != 0:
+        raise PhantGpuError(rc, "shard_range")
+    return lo.value, hi.value
+
+
+def sharded_bitmap_words(n, world):
+    return int(_lib().phant_gpu_sharded_bitmap_words(n, world))
+
+
+def nibble_owner(nibble, world):
+    return int(_lib().phant_gpu_nibble_owner(nibble, world))
 
 
 def abi_version():

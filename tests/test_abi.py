@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     assert set(declared_symbols()) == set(gpu.EXPORTS)
-    assert gpu.abi_version() == 1
+    assert gpu.abi_version() == 2
 
 
 def test_strerror_covers_all_codes():

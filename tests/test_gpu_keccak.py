@@ -115,3 +115,30 @@ def test_fixture_header_hashes(ctx, golden):
     data, off = oracle_lib.csr([bytes.fromhex(b["header_rlp"]) for b in blocks], np.uint64)
     got = gpu_hash(ctx, np.concatenate([data, np.zeros(32, np.uint8)]), off)
     assert [h.tobytes().hex() for h in got] == [b["hash"] for b in blocks] and len(blocks) == 87
+
+
+def test_regrouping_by_block_count_is_a_permutation(oracle):
+    """The two-launch counting sort that regroups messages by rate-block count (keccak_class_kernel /
+    keccak_regroup_kernel) must visit every message exactly once: 700k messages of 0..2500 bytes (1..19 blocks, i.e. all
+    16 classes incl. the clamped one), poisoned output buffer, device pointers, twice in a row on one context."""
+    import torch
+    from phant_b200 import gpu
+    rng = np.random.default_rng(77)
+    n = 700_000
+    lens = rng.integers(0, 2501, n)
+    lens[rng.random(n) < 0.5] = 532
+    lens[rng.random(n) < 0.2] = 112
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens).astype(np.uint64)
+    data = rng.integers(0, 256, int(off[-1]) + 64, dtype=np.uint8)
+    want = oracle.keccak256_batch(data, off, threads=8)
+    ctx = gpu.Context(0, gpu.FLAG_DEVICE_PTRS)
+    d_data = torch.from_numpy(data).cuda()
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    for _ in range(2):
+        d_out = torch.full((n, 32), 0xEE, dtype=torch.uint8, device="cuda")
+        ctx.keccak256_batch(d_data, d_off, n, d_out)
+        ctx.synchronize()
+        assert (d_out.cpu().numpy() == want).all()
+    assert ctx.stats()["keccak_perms"] == 2 * int((lens // 136 + 1).sum())
+    ctx.close()

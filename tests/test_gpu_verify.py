@@ -297,3 +297,109 @@ def test_proof_kat_without_the_oracle(golden):
             if c["status"] == 1:
                 assert nodes[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes().hex() == c["value"], c["name"]
     ctx.close()
+
+
+def _rlp_items(b):
+    """payload items of one RLP list (used on the proven account body: nonce, balance, storage root, code hash)"""
+    assert b[0] >= 0xc0
+    if b[0] <= 0xf7:
+        o, end = 1, 1 + b[0] - 0xc0
+    else:
+        ll = b[0] - 0xf7
+        o, end = 1 + ll, 1 + ll + int.from_bytes(b[1:1 + ll], "big")
+    assert end == len(b)
+    out = []
+    while o < end:
+        c = b[o]
+        if c < 0x80:
+            out.append(b[o:o + 1]); o += 1
+        elif c <= 0xb7:
+            out.append(b[o + 1:o + 1 + c - 0x80]); o += 1 + c - 0x80
+        else:
+            ll = c - 0xb7
+            n = int.from_bytes(b[o + 1:o + 1 + ll], "big")
+            out.append(b[o + 1 + ll:o + 1 + ll + n]); o += 1 + ll + n
+    return out
+
+
+def test_every_fixture_account_and_storage_slot_under_the_fixture_roots(ctx, oracle, golden):
+    """SURVEY.md 8c anchor, complete: ONE batch with an inclusion proof for every account of all 91 fixture pre/post
+    tables plus absent keys, verified under the stateRoot THE FIXTURE states (genesisBlockHeader.stateRoot / last valid
+    blockHeader.stateRoot) -- the expected status comes from the fixture, not from the oracle walk; then ONE batch with
+    every storage slot of every account, verified under the storageRoot the GPU just proved inside that account's leaf
+    (account proof -> storage_root -> slot proof), plus one absent slot per storage trie."""
+    from helpers import rlp_int_be
+    g = golden("fixture_states.json.gz")
+    root_of = {}
+    for t in g["tests"]:
+        for tab, root in ((t["pre"], t["pre_root"]), (t["post"], t["post_root"])):
+            assert root_of.setdefault(tab, root) == root
+    assert set(root_of) == set(g["tables"])  # every table is pinned by a header field
+    rng = np.random.default_rng(21)
+    proofs, expect, want_val, slot_jobs = [], [], [], []
+    for tab, accounts in sorted(g["tables"].items()):
+        froot = bytes.fromhex(root_of[tab])
+        if not accounts:
+            absent = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+            proofs.append(([], absent, froot)); expect.append(2); want_val.append(None)   # empty trie: keccak(0x80)
+            continue
+        items = secure_account_items(oracle.keccak256, oracle.mptize, accounts)
+        trie = oracle.trie(items)            # used to CUT the proofs; what they must hash up to is the fixture's root
+        by_key = {oracle.keccak256(bytes.fromhex(a["address"])): a for a in accounts}
+        for k, v in items:
+            if any(int(x, 16) for x in by_key[k]["storage"].values()):
+                slot_jobs.append((len(proofs), by_key[k]))
+            proofs.append((trie.prove(k), k, froot)); expect.append(1); want_val.append(v)
+        for _ in range(2):
+            k = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+            if k not in by_key:
+                proofs.append((trie.prove(k), k, froot)); expect.append(2); want_val.append(None)
+    nodes, node_off, first, keys, roots = batch_of(proofs)
+    bitmap, status, voff, vlen = gpu_verify(ctx, nodes, node_off, first, keys, roots)
+    assert (status == np.array(expect, np.uint8)).all(), np.nonzero(status != np.array(expect))[0][:10]
+    bits = np.unpackbits(bitmap.view(np.uint8), bitorder="little")[:len(proofs)]
+    assert bits.all()
+    n_acc = 0
+    for i, v in enumerate(want_val):
+        if v is not None:
+            assert nodes[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes() == v
+            n_acc += 1
+    assert n_acc >= 1100, n_acc
+    # ---- storage slots under the storage roots proven above ----
+    sproofs, sexpect, sval = [], [], []
+    for i, a in slot_jobs:
+        body = nodes[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes()
+        sroot = _rlp_items(body)[2]
+        assert len(sroot) == 32
+        st = sorted((oracle.keccak256(bytes.fromhex(k)), rlp_int_be(bytes.fromhex(v))) for k, v in a["storage"].items() if int(v, 16) != 0)
+        trie = oracle.trie(st)
+        for k, v in st:
+            sproofs.append((trie.prove(k), k, sroot)); sexpect.append(1); sval.append(v)
+        absent = oracle.keccak256(b"absent slot" + a["address"].encode())
+        sproofs.append((trie.prove(absent), absent, sroot)); sexpect.append(2); sval.append(None)
+    assert sum(e == 1 for e in sexpect) >= 70
+    nodes, node_off, first, keys, roots = batch_of(sproofs)
+    bitmap, status, voff, vlen = gpu_verify(ctx, nodes, node_off, first, keys, roots)
+    assert (status == np.array(sexpect, np.uint8)).all()
+    for i, v in enumerate(sval):
+        if v is not None:
+            assert nodes[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes() == v
+    # and the same two batches give the same answers on the oracle (the fixture decided; the oracle must agree)
+    want = oracle.verify_proofs(nodes, node_off, first, keys, roots, threads=4)
+    assert (want[1] == status).all()
+
+
+@pytest.mark.parametrize("which,n,chunk", [(2, 1_000_000, 250_000), (3, 1_200_000, 300_000)])
+def test_full_size_status_and_values_vs_oracle(ctx, oracle, which, n, chunk):
+    """BASELINE sizes against the ORACLE, not a pattern: 1M account proofs (C2) and 1.2M storage proofs (C3), every status,
+    accept bit and value slice compared with oracle.verify_proofs chunk by chunk (the oracle generator regenerates each
+    chunk from (seed, index); the host-pointer ABI verifies it)."""
+    for lo in range(0, n, chunk):
+        o = oracle.synth_c2(chunk, depth=8, first=lo, threads=8) if which == 2 else oracle.synth_c3(chunk, first=lo, threads=8)
+        want = oracle.verify_proofs(*o, threads=8)
+        got = gpu_verify(ctx, *o)
+        assert (got[1] == want[1]).all() and (got[0] == want[0]).all()
+        ok = want[1] == 1
+        assert ok.sum() > 0.98 * chunk
+        assert (got[2][ok] == want[2][ok]).all() and (got[3][ok] == want[3][ok]).all()
+        assert (want[1] == np.where((np.arange(chunk) + lo) % 97 == 0, 0, 1)).all()
