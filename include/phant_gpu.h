@@ -58,6 +58,8 @@ typedef struct {
     uint64_t reserved[4];
 } phant_gpu_config;
 
+/* Environment overrides read by phant_gpu_create: PHANT_GPU_DEVICE (replaces cfg->device), PHANT_GPU_FLAGS (decimal / 0x..,
+ * OR-ed into cfg->flags), PHANT_GPU_NCCL_LIB (NCCL library name for the multi-GPU entry points). */
 int phant_gpu_abi_version(void);
 int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg);
 void phant_gpu_destroy(phant_gpu_ctx* ctx);

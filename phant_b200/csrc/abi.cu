@@ -7,6 +7,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -99,7 +100,12 @@ extern "C" int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return PHANT_GPU_E_NO_DEVICE; }
-    const int dev = cfg ? cfg->device : 0;
+    // environment overrides (deployment knobs a Zig host need not plumb through): PHANT_GPU_DEVICE replaces cfg->device,
+    // PHANT_GPU_FLAGS (decimal or 0x..) is OR-ed into cfg->flags; PHANT_GPU_NCCL_LIB names the NCCL library (comm.cu)
+    int dev = cfg ? cfg->device : 0;
+    uint32_t env_flags = 0;
+    if (const char* e = getenv("PHANT_GPU_DEVICE")) { char* end = nullptr; const long v = strtol(e, &end, 10); if (end != e && *end == 0) dev = (int)v; }
+    if (const char* e = getenv("PHANT_GPU_FLAGS")) { char* end = nullptr; const unsigned long v = strtoul(e, &end, 0); if (end != e && *end == 0) env_flags = (uint32_t)v; }
     if (dev < 0 || dev >= count) return PHANT_GPU_E_INVALID;
     if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return PHANT_GPU_E_NO_DEVICE; }
     cudaDeviceProp prop;
@@ -108,7 +114,7 @@ extern "C" int phant_gpu_create(phant_gpu_ctx** out, const phant_gpu_config* cfg
     phant_gpu_ctx* ctx = new (std::nothrow) phant_gpu_ctx();
     if (!ctx) return PHANT_GPU_E_OOM;
     ctx->device = dev;
-    ctx->flags = cfg ? cfg->flags : 0;
+    ctx->flags = (cfg ? cfg->flags : 0) | env_flags;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
@@ -197,6 +203,7 @@ int phant_gpu_ctx::hash_csr(const uint8_t* d_msgs, const uint64_t* d_off, uint64
     phant_gpu_ctx* ctx = this;
     if (n == 0) return PHANT_GPU_OK;
     if (n > 0xffffffffull) return PHANT_GPU_E_INVALID; // message indices are 32-bit on the device
+    NvtxRange nvtx("phant:keccak");
     KeccakVariant variant = KECCAK_STAGED;
     if (flags & PHANT_GPU_FLAG_KECCAK_DIRECT) variant = KECCAK_DIRECT;
     if (flags & PHANT_GPU_FLAG_KECCAK_WARP) variant = KECCAK_WARP;
@@ -363,6 +370,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         if (int rc = ctx->d_digests.reserve(ctx, 32 * n_nodes + 32)) return rc;
         if (int rc = ctx->d_summary.reserve(ctx, 4 * n_nodes + 32)) return rc;
         if (int rc = ctx->hash_csr(in->nodes, in->node_off, n_nodes, total, (uint8_t*)ctx->d_digests.ptr, (uint32_t*)ctx->d_summary.ptr)) return rc;
+        NvtxRange nvtx("phant:walk");
         if (int rc = ctx->wait_walk_fence()) return rc; // sharded call: the previous gather of this bitmap buffer (comm.cu)
         if (accept_bitmap) CU(cudaMemsetAsync(accept_bitmap, 0, bm_bytes, ctx->stream));
         ctx->time_begin(1);
@@ -432,6 +440,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
                 return PHANT_GPU_E_INVALID;
             }
         }
+        nvtxRangePushA("phant:h2d chunk");
         if (b1 > b0) CU(cudaMemcpyAsync(d_nodes + b0, in->nodes + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
         CU(cudaMemcpyAsync(d_noff + n0, in->node_off + n0, 8 * (n1 - n0 + 1), cudaMemcpyHostToDevice, cs));
         CU(cudaMemcpyAsync(d_pfirst + p0, in->proof_first + p0, 8 * (p1 - p0 + 1), cudaMemcpyHostToDevice, cs));
@@ -440,6 +449,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         if (ctx->chunk_events.size() <= chunk) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_events.push_back(e); }
         CU(cudaEventRecord(ctx->chunk_events[chunk], cs));
         CU(cudaStreamWaitEvent(s, ctx->chunk_events[chunk], 0));
+        nvtxRangePop();
         if (int rc = ctx->hash_csr(d_nodes, d_noff + n0, n1 - n0, b1 - b0, (uint8_t*)ctx->d_digests.ptr + 32 * n0,
                                    (uint32_t*)ctx->d_summary.ptr + n0)) {
             cudaStreamSynchronize(cs); // as above: no DMA on the caller's buffers after we return

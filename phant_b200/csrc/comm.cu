@@ -281,6 +281,7 @@ extern "C" int phant_gpu_verify_proofs_sharded(phant_gpu_ctx* ctx, const phant_g
         if (world == 1) return PHANT_GPU_OK;
         const uint64_t my_words = (hi - lo + 63) / 64;
         if (my_words < per_words) CU(cudaMemsetAsync(mine + my_words, 0, 8 * (per_words - my_words), ctx->stream)); // short / empty last shard
+        NvtxRange nvtx("phant:gather");
         cudaEvent_t done = fence_for(ctx, global_bitmap);
         if (!done) return PHANT_GPU_E_CUDA;
         CU(cudaEventRecord(ctx->ev_compute, ctx->stream));

@@ -7,6 +7,14 @@
 #include <array>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+// NVTX ranges around the phases of a call (H2D staging, hash, walk, gather): free when no tool is attached (header-only
+// NVTX v3 resolves its injection library lazily), visible in nsys / ncu --nvtx timelines
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct phant_gpu_ctx;
 
 struct DevBuf {

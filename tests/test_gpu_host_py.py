@@ -253,3 +253,42 @@ def test_payload_witness_blob(ctx, oracle, golden):
     assert host.verify_payload_witness(ctx, trie.root(), host.encode_witness([], [], dmg), keys)[7] in (0, 3)
     with pytest.raises(host.InvalidWitness):
         host.verify_payload_witness(ctx, trie.root(), blob[:-1], keys)
+
+
+def test_new_payload_v2_on_the_device(ctx, oracle, golden):
+    """N2 end to end through the REAL library (execution_payload.zig:125-183 with its TODO filled in): the payload's two index
+    tries as one forest (M), the witness blob decoded and every touched key resolved in its node set from the parent state
+    root (W), all senders in one recovery call (R).  Same scenario as the CPU test of the host logic
+    (tests/test_host_witness.py), here nothing stands in for the GPU.  The witness is cut from a fixture state whose root the
+    fixture header pins; the transactions are the reference's mainnet vectors (signer.zig:199-227, transaction.zig:282-303)."""
+    from phant_b200 import host
+    from helpers import secure_account_items
+    g = golden("fixture_states.json.gz")
+    root_of = {t["pre"]: t["pre_root"] for t in g["tests"]}
+    tab = max((k for k in g["tables"] if k in root_of), key=lambda k: len(g["tables"][k]))
+    accounts = g["tables"][tab]
+    items = secure_account_items(oracle.keccak256, oracle.mptize, accounts)
+    trie = oracle.trie(items)                                   # cuts the witness; the root it must reach is the fixture's
+    state_root = bytes.fromhex(root_of[tab])
+    keys = [k for k, _ in items[:40]] + [oracle.keccak256(b"nobody"), oracle.keccak256(b"nobody else")]
+    nodes = list({nd: 1 for k in keys for nd in trie.prove(k)})
+    kat = golden("ecrecover_kat.json")["txs"]
+    txs = [bytes.fromhex(t["encoded"]) for t in kat]
+    wds = [host._rlp_list([host._rlp_uint(i), host._rlp_uint(7), host._rlp_str(bytes(20)), host._rlp_uint(1000 + i)]) for i in range(5)]
+    r = host.new_payload_v2(ctx, txs, wds, host.encode_witness([], [], nodes), state_root, keys, chain_id=1)
+    assert r["accept"] and r["witness_status"] == [1] * 40 + [2, 2]
+    assert [a.hex() for a in r["senders"]] == [t["sender"] for t in kat]
+    assert r["transactions_root"] == oracle.mptize([(i.to_bytes(32, "big"), t) for i, t in enumerate(txs)])
+    assert r["withdrawals_root"] == oracle.mptize([(i.to_bytes(32, "big"), w) for i, w in enumerate(wds)])
+    # an incomplete witness, a wrong parent root and an undecodable blob all refuse the payload before execution
+    short = host.new_payload_v2(ctx, txs, wds, host.encode_witness([], [], nodes[1:]), state_root, keys)
+    assert not short["accept"] and set(short["witness_status"]) & {0, 3}
+    wrong = host.new_payload_v2(ctx, txs, wds, host.encode_witness([], [], nodes), bytes([state_root[0] ^ 1]) + state_root[1:], keys)
+    assert not wrong["accept"] and set(wrong["witness_status"]) == {3}   # the root node is not in the set
+    broken = host.new_payload_v2(ctx, txs, wds, b"\xc1", state_root, keys)
+    assert not broken["accept"] and broken["witness_error"]
+    # the reference's own sample request (src/engine_api/test_req.json via engine_api.zig:87-134): no transactions, no
+    # withdrawals -> both roots are the empty-trie constant its receiptsRoot field also shows
+    p = golden("engine_payload_kat.json")["payload"]
+    e = host.new_payload_v2(ctx, [bytes.fromhex(t[2:]) for t in p["transactions"]], [])
+    assert e["accept"] and e["transactions_root"] == e["withdrawals_root"] == host.EMPTY_MPT_ROOT == bytes.fromhex(p["receiptsRoot"][2:])
