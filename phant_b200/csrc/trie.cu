@@ -1106,11 +1106,14 @@ extern "C" int phant_gpu_state_subtree_roots(phant_gpu_ctx* ctx, const phant_gpu
 // ------------------------------------------------------------------------------------------------
 // U: resident complete trie
 // ------------------------------------------------------------------------------------------------
+struct SparseTrie;
 struct phant_gpu_trie {
     phant_gpu_ctx* ctx;
+    uint32_t kind = 0;
     uint32_t depth;
-    std::vector<uint8_t*> level; // level[l] = 16^l hashes
+    std::vector<uint8_t*> level; // kind 0: level[l] = 16^l hashes
     DevBuf store, work;
+    SparseTrie* sp = nullptr;    // kind 1
 };
 
 namespace {
@@ -1365,10 +1368,557 @@ int ctrie_hash_level(phant_gpu_trie* t, uint32_t l, const uint32_t* d_parents, u
 
 } // namespace
 
+// ------------------------------------------------------------------------------------------------
+// U kind 1: a SPARSE resident secure trie (32-byte keys, arbitrary values) -- the structure behind StateDB.root() for a real
+// state (hook src/blockchain/blockchain.zig:83-85): after a block only the dirty part is re-hashed.
+//
+// Resident on the device:  the sorted key table (32 B per key) with a value record (offset, length) into an append-only
+// value arena, and a DENSE TOP of L nibble levels: level d holds the 16^d node references of depth d.  Level L's entries
+// are the roots of the 16^L BUCKETS -- the sparse subtrees of the keys sharing an L-nibble prefix.  Keys are Keccak
+// outputs, so with 16..256 keys per bucket (L = floor(log16(n / 16))) every node above the buckets is a real branch with
+// >= 2 children and needs no extension / collapse logic; this is CHECKED on the device at every update, and when it does
+// not hold (adversarial or tiny key sets) L is lowered and the top rebuilt -- L = 0 is one bucket = a plain rebuild.
+//
+// An update (upserts; an empty value deletes): sort the dirty keys, merge them into the table (positions by lower bound +
+// two scans), re-build ONLY the dirty buckets as one forest with the M builder (build_forest with start_depth = L: leaves,
+// extensions, embedded nodes and all of mptize's rules apply inside a bucket), then re-hash the dirty frontier of the L
+// dense levels bottom-up (one launch per level, variable child masks).  Pure value updates skip the merge.
+// ------------------------------------------------------------------------------------------------
+struct SRec { uint64_t off; uint32_t len; uint32_t pad; };
+
+struct SparseTrie {
+    uint64_t n = 0;
+    DevBuf keys[2], recs[2]; // sorted keys / records, ping-pong across merges
+    int cur = 0;
+    DevBuf arena;
+    uint64_t arena_used = 0;
+    uint32_t L = 0;
+    DevBuf top, present;     // levels 0..L: 32-byte reference + presence byte per node; level d starts at node (16^d - 1) / 15
+    DevBuf sa, sb, sc, sd, se, sf, sg, sh, sroots, ssort; // scratch
+    uint8_t root[32];
+    uint64_t updates = 0, rebuilds = 0;
+};
+
+namespace {
+
+constexpr uint8_t EMPTY_ROOT_H[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                      0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+
+inline uint64_t level_base(uint32_t d) { return ((1ull << (4 * d)) - 1) / 15; }
+
+__device__ __forceinline__ int cmp_key32(const uint8_t* a, const uint8_t* b)
+{
+    const uint4 a0 = *reinterpret_cast<const uint4*>(a), a1 = *reinterpret_cast<const uint4*>(a + 16);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(b), b1 = *reinterpret_cast<const uint4*>(b + 16);
+    const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t x = __byte_perm(aw[i], 0, 0x0123), y = __byte_perm(bw[i], 0, 0x0123); // big-endian order
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
+}
+__device__ __forceinline__ uint32_t key_prefix(const uint8_t* key, uint32_t L) // first L <= 7 nibbles as an integer
+{
+    const uint32_t w = __byte_perm(*reinterpret_cast<const uint32_t*>(key), 0, 0x0123);
+    return L ? w >> (32 - 4 * L) : 0;
+}
+
+// dirty keys (sorted): position in the table, whether found; classification into replace / insert / delete
+__global__ void st_classify_kernel(const uint8_t* __restrict__ table, uint32_t n, const uint8_t* __restrict__ dk, const uint32_t* __restrict__ dlen,
+                                   uint32_t m, uint32_t* __restrict__ lb, uint8_t* __restrict__ kind /*0 no-op, 1 replace, 2 insert, 3 delete*/,
+                                   uint32_t* __restrict__ del_flag /*n, nullable when n == 0*/, uint32_t* __restrict__ ins_at /*n+1*/,
+                                   uint32_t* __restrict__ ins_flag /*m*/, uint64_t* __restrict__ app_size /*m*/, uint32_t* __restrict__ counters)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const uint8_t* q = dk + 32ull * j;
+        uint32_t a = 0, b = n;
+        while (a < b) {
+            const uint32_t mid = (a + b) >> 1;
+            if (cmp_key32(table + 32ull * mid, q) < 0) a = mid + 1; else b = mid;
+        }
+        const bool found = a < n && cmp_key32(table + 32ull * a, q) == 0;
+        const bool del = dlen[j] == 0;
+        uint8_t k = 0;
+        if (found) k = del ? 3 : 1; else k = del ? 0 : 2;
+        lb[j] = a;
+        kind[j] = k;
+        ins_flag[j] = k == 2;
+        app_size[j] = k == 1 || k == 2 ? dlen[j] : 0;
+        if (k == 3) { del_flag[a] = 1; atomicAdd(&counters[1], 1u); }
+        if (k == 2) { atomicAdd(&ins_at[a], 1u); atomicAdd(&counters[0], 1u); }
+        if (j + 1 < m && cmp_key32(q, dk + 32ull * (j + 1)) == 0) counters[2] = 1; // duplicate key in one update
+    }
+}
+// append the new values to the arena; replaced records are rewritten in place
+__global__ void st_gather_voff_kernel(const uint32_t* __restrict__ raw_voff, const uint32_t* __restrict__ perm, uint32_t m, uint32_t* __restrict__ dvoff,
+                                      uint32_t* __restrict__ dlen)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const uint32_t src = perm[j];
+        dvoff[j] = raw_voff[src];
+        dlen[j] = raw_voff[src + 1] - raw_voff[src];
+    }
+}
+__global__ void st_append_kernel(const uint8_t* __restrict__ dv, const uint32_t* __restrict__ dvoff, const uint32_t* __restrict__ dlen,
+                                 const uint8_t* __restrict__ kind, const uint32_t* __restrict__ lb, const uint64_t* __restrict__ app_off, uint32_t m, uint64_t arena_base,
+                                 uint8_t* __restrict__ arena, SRec* __restrict__ recs_cur, SRec* __restrict__ drec)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < m; j += warps) {
+        const uint8_t k = kind[j];
+        if (k != 1 && k != 2) continue;
+        const uint32_t len = dlen[j];
+        const uint64_t dst = arena_base + app_off[j];
+        for (uint32_t b = lane; b < len; b += 32) arena[dst + b] = dv[dvoff[j] + b];
+        if (lane == 0) {
+            const SRec r{dst, len, 0};
+            drec[j] = r;
+            if (k == 1) recs_cur[lb[j]] = r;
+        }
+    }
+}
+__global__ void st_keep_kernel(const uint32_t* __restrict__ del_flag, uint32_t n, uint32_t* __restrict__ keep /*n+1, keep[n] = 0*/)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) keep[i] = i < n && !del_flag[i] ? 1 : 0;
+}
+// merged table: kept table entries and inserts at their final positions
+__global__ void st_merge_table_kernel(const uint8_t* __restrict__ keys, const SRec* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ del_flag,
+                                      const uint32_t* __restrict__ K /*excl scan of keep, n*/, const uint32_t* __restrict__ I /*excl scan of ins_at, n+2*/,
+                                      uint8_t* __restrict__ keys_out, SRec* __restrict__ recs_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (del_flag[i]) continue;
+        const uint32_t p = K[i] + I[i + 1];
+        const uint4* s = reinterpret_cast<const uint4*>(keys + 32ull * i);
+        uint4* d = reinterpret_cast<uint4*>(keys_out + 32ull * p);
+        d[0] = s[0]; d[1] = s[1];
+        recs_out[p] = recs[i];
+    }
+}
+__global__ void st_merge_dirty_kernel(const uint8_t* __restrict__ dk, const SRec* __restrict__ drec, const uint8_t* __restrict__ kind,
+                                      const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ins_index, uint32_t m, uint32_t n,
+                                      const uint32_t* __restrict__ K /*n+1 entries valid: K[n] = kept total*/, uint8_t* __restrict__ keys_out,
+                                      SRec* __restrict__ recs_out)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        if (kind[j] != 2) continue;
+        const uint32_t p = K[lb[j]] + ins_index[j];
+        const uint4* s = reinterpret_cast<const uint4*>(dk + 32ull * j);
+        uint4* d = reinterpret_cast<uint4*>(keys_out + 32ull * p);
+        d[0] = s[0]; d[1] = s[1];
+        recs_out[p] = drec[j];
+    }
+}
+// bucket of each dirty key + "first of its bucket" flag
+__global__ void st_bucket_flag_kernel(const uint8_t* __restrict__ dk, uint32_t m, uint32_t L, uint32_t* __restrict__ bucket, uint32_t* __restrict__ first)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const uint32_t b = key_prefix(dk + 32ull * j, L);
+        bucket[j] = b;
+        first[j] = j == 0 || key_prefix(dk + 32ull * (j - 1), L) != b;
+    }
+}
+__global__ void st_compact_kernel(const uint32_t* __restrict__ val, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t m,
+                                  uint32_t* __restrict__ out)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x)
+        if (flag[j]) out[pos[j]] = val[j];
+}
+// table range of each listed bucket (nullptr list = bucket u itself)
+__global__ void st_bucket_range_kernel(const uint8_t* __restrict__ table, uint32_t n, uint32_t L, const uint32_t* __restrict__ list, uint32_t nb,
+                                       uint32_t* __restrict__ lo_out, uint32_t* __restrict__ cnt_out)
+{
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nb; u += gridDim.x * blockDim.x) {
+        const uint32_t b = list ? list[u] : u;
+        uint32_t r[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const uint32_t want = b + e;
+            uint32_t lo = 0, hi = n;
+            if (L == 0) lo = e ? n : 0;
+            else while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (key_prefix(table + 32ull * mid, L) < want) lo = mid + 1; else hi = mid;
+            }
+            r[e] = lo;
+        }
+        lo_out[u] = r[0];
+        cnt_out[u] = r[1] - r[0];
+    }
+}
+// gather the keys of the listed buckets into a contiguous forest input (warp per bucket)
+__global__ void st_gather_keys_kernel(const uint8_t* __restrict__ table, const SRec* __restrict__ recs, const uint32_t* __restrict__ lo,
+                                      const uint32_t* __restrict__ seg_off, uint32_t nb, uint8_t* __restrict__ gkeys, uint32_t* __restrict__ gkey_off,
+                                      uint32_t* __restrict__ seg_of_key, uint64_t* __restrict__ gval_size, SRec* __restrict__ grec)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < nb; u += warps) {
+        const uint32_t base = seg_off[u], cnt = seg_off[u + 1] - base, from = lo[u];
+        for (uint32_t t = lane; t < cnt; t += 32) {
+            const uint4* s = reinterpret_cast<const uint4*>(table + 32ull * (from + t));
+            uint4* d = reinterpret_cast<uint4*>(gkeys + 32ull * (base + t));
+            d[0] = s[0]; d[1] = s[1];
+            gkey_off[base + t] = 32u * (base + t);
+            seg_of_key[base + t] = u;
+            const SRec r = recs[from + t];
+            gval_size[base + t] = r.len;
+            grec[base + t] = r;
+        }
+    }
+}
+__global__ void st_gather_vals_kernel(const uint8_t* __restrict__ arena, const SRec* __restrict__ grec, const uint64_t* __restrict__ gval_off, uint32_t mk,
+                                      uint8_t* __restrict__ gvals)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < mk; t += warps) {
+        const SRec r = grec[t];
+        const uint64_t dst = gval_off[t];
+        for (uint32_t b = lane; b < r.len; b += 32) gvals[dst + b] = arena[r.off + b];
+    }
+}
+__global__ void st_scatter_roots_kernel(const uint8_t* __restrict__ roots, const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, uint32_t nb,
+                                        uint8_t* __restrict__ level, uint8_t* __restrict__ present)
+{
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nb; u += gridDim.x * blockDim.x) {
+        const uint32_t b = list ? list[u] : u;
+        const uint4* s = reinterpret_cast<const uint4*>(roots + 32ull * u);
+        uint4* d = reinterpret_cast<uint4*>(level + 32ull * b);
+        d[0] = s[0]; d[1] = s[1];
+        present[b] = cnt[u] ? 1 : 0;
+    }
+}
+__global__ void st_parent_flag_kernel(const uint32_t* __restrict__ child, uint32_t cnt, uint32_t* __restrict__ parent, uint32_t* __restrict__ first)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+        parent[j] = child[j] >> 4;
+        first[j] = j == 0 || (child[j - 1] >> 4) != (child[j] >> 4);
+    }
+}
+// One dense-top node per thread: rlp([ref or "" x 16, ""]) over the children that exist (src/mpt/mpt.zig:218-247), built in the
+// thread's shared-memory slot, hashed with the product sponge.  A node with exactly ONE child would have to collapse into
+// an extension / its child (mpt.zig:83-106): that breaks the dense-top premise and is reported through *violation.
+__global__ void __launch_bounds__(FR_WARPS * 32)
+st_top_branch_kernel(const uint8_t* __restrict__ child_level, const uint8_t* __restrict__ child_present, const uint32_t* __restrict__ parents /*nullable*/,
+                     uint32_t count, uint8_t* __restrict__ level, uint8_t* __restrict__ present, uint32_t* __restrict__ violation)
+{
+    extern __shared__ __align__(16) uint8_t fr_smem[];
+    const uint32_t slot = (uint32_t)__cvta_generic_to_shared(fr_smem) + threadIdx.x * FR_SLOT;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t p = parents ? parents[i] : i;
+        uint32_t mask = 0;
+        for (uint32_t v = 0; v < 16; ++v) mask |= (child_present[16ull * p + v] ? 1u : 0u) << v;
+        const uint32_t c = __popc(mask);
+        if (c == 0) { present[p] = 0; continue; }
+        if (c == 1) atomicExch(violation, 1u);
+        present[p] = 1;
+        const uint32_t payload = 33 * c + (16 - c) + 1;
+        uint32_t sa = slot;
+        if (payload <= 55) sts8(sa++, 0xc0 + payload);
+        else if (payload < 256) { sts8(sa++, 0xf8); sts8(sa++, payload); }
+        else { sts8(sa++, 0xf9); sts8(sa++, payload >> 8); sts8(sa++, payload & 255); }
+        for (uint32_t v = 0; v < 16; ++v) {
+            if (!((mask >> v) & 1)) { sts8(sa++, 0x80); continue; }
+            sts8(sa++, 0xa0);
+            const uint4* h = reinterpret_cast<const uint4*>(child_level + 32ull * (16ull * p + v));
+            const uint4 a = h[0], b = h[1];
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sts8(sa++, w[k] & 255); sts8(sa++, (w[k] >> 8) & 255); sts8(sa++, (w[k] >> 16) & 255); sts8(sa++, w[k] >> 24); }
+        }
+        sts8(sa++, 0x80);
+        const uint32_t len = sa - slot;
+        uint64_t st[25];
+#pragma unroll
+        for (int q = 0; q < 25; ++q) st[q] = 0;
+        uint32_t at = slot, rem = len;
+        while (rem >= 136) { absorb_full_smem<2>(st, at); at += 136; rem -= 136; }
+        absorb_final_smem<2>(st, at, rem, slot + FR_SLOT - at);
+        uint4* o = reinterpret_cast<uint4*>(level + 32ull * p);
+        o[0] = make_uint4((uint32_t)st[0], (uint32_t)(st[0] >> 32), (uint32_t)st[1], (uint32_t)(st[1] >> 32));
+        o[1] = make_uint4((uint32_t)st[2], (uint32_t)(st[2] >> 32), (uint32_t)st[3], (uint32_t)(st[3] >> 32));
+    }
+}
+
+int st_scan_u32(phant_gpu_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t cnt)
+{
+    size_t temp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, out, (int64_t)cnt, ctx->stream));
+    RC(ctx->d_cub.reserve(ctx, temp));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->d_cub.ptr, temp, in, out, (int64_t)cnt, ctx->stream));
+    return 0;
+}
+
+uint32_t st_target_L(uint64_t n)
+{
+    uint32_t L = 0;
+    while (L < 6 && (n >> (4 * (L + 1))) >= 16) ++L; // 16 .. 255 keys per bucket
+    return L;
+}
+
+// (re)build the listed buckets (d_list == nullptr: all 16^L of them) and the dense levels above them; root -> sp->root
+int st_rebuild(phant_gpu_trie* t, const uint32_t* d_list, uint32_t nb, bool all)
+{
+    phant_gpu_ctx* ctx = t->ctx;
+    SparseTrie* sp = t->sp;
+    cudaStream_t s = ctx->stream;
+    const int dev = ctx->device;
+    const uint32_t L = sp->L, n = (uint32_t)sp->n;
+    const uint8_t* table = (const uint8_t*)sp->keys[sp->cur].ptr;
+    const SRec* recs = (const SRec*)sp->recs[sp->cur].ptr;
+    uint8_t* top = (uint8_t*)sp->top.ptr;
+    uint8_t* pres = (uint8_t*)sp->present.ptr;
+    if (n == 0) { memcpy(sp->root, EMPTY_ROOT_H, 32); return PHANT_GPU_OK; }
+    // ranges and sizes of the buckets
+    RC(sp->sa.reserve(ctx, 4ull * (nb + 2) * 3 + 64));
+    uint32_t* lo = (uint32_t*)sp->sa.ptr;
+    uint32_t* cnt = lo + nb + 2;
+    uint32_t* seg_off = cnt + nb + 2;
+    st_bucket_range_kernel<<<grid1d(dev, nb, 128), 128, 0, s>>>(table, n, L, d_list, nb, lo, cnt);
+    CU(cudaMemsetAsync(cnt + nb, 0, 4, s));
+    RC(st_scan_u32(ctx, cnt, seg_off, nb + 1));
+    uint32_t mk = 0;
+    CU(cudaMemcpyAsync(&mk, seg_off + nb, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    ctx->stats.launches += 2;
+    RC(sp->sroots.reserve(ctx, 32ull * nb + 64));
+    if (mk) {
+        RC(sp->sb.reserve(ctx, 32ull * mk + 64));                       // gathered keys
+        RC(sp->sc.reserve(ctx, 4ull * (mk + 2) * 2 + 8ull * (mk + 2) * 2 + 16ull * mk + 64));
+        uint8_t* gkeys = (uint8_t*)sp->sb.ptr;
+        uint64_t* gsize = (uint64_t*)sp->sc.ptr;
+        uint64_t* gvoff = gsize + mk + 2;
+        SRec* grec = (SRec*)(gvoff + mk + 2);
+        uint32_t* gkoff = (uint32_t*)(grec + mk);
+        uint32_t* seg_of_key = gkoff + mk + 2;
+        st_gather_keys_kernel<<<grid1d(dev, nb, 256, 32), 256, 0, s>>>(table, recs, lo, seg_off, nb, gkeys, gkoff, seg_of_key, gsize, grec);
+        const uint32_t last = 32u * mk;
+        CU(cudaMemcpyAsync(gkoff + mk, &last, 4, cudaMemcpyHostToDevice, s));
+        RC(scan_sizes(ctx, gsize, gvoff, mk));
+        uint64_t vbytes = 0;
+        CU(cudaMemcpyAsync(&vbytes, gvoff + mk, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        RC(sp->sd.reserve(ctx, vbytes + 64));
+        st_gather_vals_kernel<<<grid1d(dev, mk, 256, 32), 256, 0, s>>>((const uint8_t*)sp->arena.ptr, grec, gvoff, mk, (uint8_t*)sp->sd.ptr);
+        ctx->stats.launches += 3;
+        RC(ctx->build_forest(gkeys, gkoff, (const uint8_t*)sp->sd.ptr, gvoff, mk, seg_off, nb, seg_of_key, (uint8_t*)sp->sroots.ptr, -1, L));
+    }
+    if (L == 0) { // one bucket: its root is the trie's root
+        CU(cudaMemcpyAsync(sp->root, sp->sroots.ptr, 32, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return PHANT_GPU_OK;
+    }
+    st_scatter_roots_kernel<<<grid1d(dev, nb, 256), 256, 0, s>>>((const uint8_t*)sp->sroots.ptr, d_list, cnt, nb, top + 32 * level_base(L), pres + level_base(L));
+    ctx->stats.launches++;
+    // dense levels bottom-up: parents of the dirty children
+    static bool attr[64] = {false};
+    bool& opted = attr[(dev >= 0 && dev < 64) ? dev : 0];
+    if (!opted) { CU(cudaFuncSetAttribute(st_top_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM)); opted = true; }
+    RC(sp->se.reserve(ctx, 4ull * (nb + 2) * 5 + 64));
+    uint32_t* par = (uint32_t*)sp->se.ptr;
+    uint32_t* flag = par + nb + 2;
+    uint32_t* pos = flag + nb + 2;
+    uint32_t* ping[2] = {pos + nb + 2, pos + 2 * (nb + 2)};
+    RC(ctx->d_b3.reserve(ctx, 64));
+    uint32_t* viol = (uint32_t*)ctx->d_b3.ptr + 12;
+    CU(cudaMemsetAsync(viol, 0, 4, s));
+    const uint32_t* child = d_list;
+    uint32_t ccount = nb;
+    const unsigned fr_cap = (unsigned)keccak_num_sms(dev) * 3;
+    for (int d = (int)L - 1; d >= 0; --d) {
+        const uint32_t* plist = nullptr;
+        uint32_t pcount = 1u << (4 * d);
+        if (!all) { // distinct parents of the (sorted) dirty children
+            uint32_t* uniq = ping[d & 1];
+            st_parent_flag_kernel<<<grid1d(dev, ccount, 256), 256, 0, s>>>(child, ccount, par, flag);
+            CU(cudaMemsetAsync(flag + ccount, 0, 4, s));
+            RC(st_scan_u32(ctx, flag, pos, ccount + 1));
+            st_compact_kernel<<<grid1d(dev, ccount, 256), 256, 0, s>>>(par, flag, pos, ccount, uniq);
+            uint32_t pc = 0;
+            CU(cudaMemcpyAsync(&pc, pos + ccount, 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            pcount = pc;
+            plist = uniq;
+            child = uniq;
+            ccount = pc;
+            ctx->stats.launches += 3;
+        }
+        const unsigned g = (pcount + FR_WARPS * 32 - 1) / (FR_WARPS * 32);
+        st_top_branch_kernel<<<g < fr_cap ? g : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(top + 32 * level_base(d + 1), pres + level_base(d + 1), plist, pcount,
+                                                                               top + 32 * level_base(d), pres + level_base(d), viol);
+        ctx->stats.launches++;
+    }
+    CU(cudaGetLastError());
+    uint32_t v = 0;
+    CU(cudaMemcpyAsync(sp->root, top, 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&v, viol, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return v ? 1 : PHANT_GPU_OK; // 1 = the dense-top premise does not hold at this L
+}
+
+int st_set_L_and_rebuild_all(phant_gpu_trie* t, uint32_t L)
+{
+    phant_gpu_ctx* ctx = t->ctx;
+    SparseTrie* sp = t->sp;
+    for (;;) {
+        sp->L = L;
+        const uint64_t nodes = level_base(L + 1);
+        RC(sp->top.reserve(ctx, 32 * nodes + 64));
+        RC(sp->present.reserve(ctx, nodes + 64));
+        CU(cudaMemsetAsync(sp->present.ptr, 0, nodes, ctx->stream));
+        sp->rebuilds++;
+        const int rc = st_rebuild(t, nullptr, 1u << (4 * L), true);
+        if (rc != 1) return rc;
+        if (L == 0) return PHANT_GPU_E_CUDA; // cannot happen: L = 0 has no dense level
+        --L; // some top node has a single child: fewer dense levels
+    }
+}
+
+int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, const uint32_t* val_off, uint64_t m64, uint8_t out_root[32])
+{
+    phant_gpu_ctx* ctx = t->ctx;
+    SparseTrie* sp = t->sp;
+    cudaStream_t s = ctx->stream;
+    const int dev = ctx->device;
+    if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) return PHANT_GPU_E_INVALID; // host tables (it is the StateDB flattening, as S)
+    if (m64 == 0) { memcpy(out_root, sp->root, 32); return PHANT_GPU_OK; }
+    if (!keys32 || !val_off || m64 >= (1ull << 28) || sp->n + m64 >= (1ull << 30)) return PHANT_GPU_E_INVALID;
+    const uint32_t m = (uint32_t)m64, n = (uint32_t)sp->n;
+    for (uint32_t i = 0; i < m; ++i)
+        if (val_off[i + 1] < val_off[i]) return PHANT_GPU_E_INVALID;
+    const uint64_t vb = val_off[m];
+    if (vb && !vals) return PHANT_GPU_E_INVALID;
+    // ---- stage + sort the dirty keys ----
+    RC(sp->sg.reserve(ctx, 32ull * m * 2 + vb + 64 + 4ull * (m + 2) * 8 + 8ull * (m + 2) * 2 + 16ull * m + m + 256));
+    uint8_t* raw_k = (uint8_t*)sp->sg.ptr;
+    uint8_t* dk = raw_k + 32ull * m;                         // sorted keys
+    uint8_t* dv = dk + 32ull * m;                            // values as given
+    uint32_t* u32 = (uint32_t*)(dv + ((vb + 63) & ~63ull));
+    uint32_t* raw_voff = u32;                                // m+1 (+1 pad)
+    uint32_t* perm = raw_voff + m + 2;
+    uint32_t* dvoff = perm + m + 2;                          // sorted: start offset; dvoff[j+1] is NOT the end (values stay in given order)
+    uint32_t* dlen = dvoff + m + 2;
+    uint32_t* lb = dlen + m + 2;
+    uint32_t* ins_flag = lb + m + 2;
+    uint32_t* ins_index = ins_flag + m + 2;
+    uint32_t* bucket = ins_index + m + 2;
+    uint64_t* app_size = (uint64_t*)(bucket + m + 2);
+    uint64_t* app_off = app_size + m + 2;
+    SRec* drec = (SRec*)(app_off + m + 2);
+    uint8_t* kind = (uint8_t*)(drec + m);
+    CU(cudaMemcpyAsync(raw_k, keys32, 32ull * m, cudaMemcpyHostToDevice, s));
+    if (vb) CU(cudaMemcpyAsync(dv, vals, vb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(raw_voff, val_off, 4ull * (m + 1), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += 32ull * m + vb + 4ull * (m + 1);
+    RC(ctx->sort_by_segment_and_hash(raw_k, nullptr, m, perm, sp->ssort));
+    gather_rows32_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(raw_k, perm, m, dk);
+    st_gather_voff_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(raw_voff, perm, m, dvoff, dlen);
+    // ---- classify against the table ----
+    RC(sp->sh.reserve(ctx, 4ull * (n + 3) * 5 + 64));
+    uint32_t* del_flag = (uint32_t*)sp->sh.ptr;
+    uint32_t* ins_at = del_flag + n + 3;
+    uint32_t* keep = ins_at + n + 3;
+    uint32_t* Kscan = keep + n + 3;
+    uint32_t* Iscan = Kscan + n + 3;
+    CU(cudaMemsetAsync(del_flag, 0, 4ull * (n + 3) * 2, s));
+    RC(ctx->d_b3.reserve(ctx, 64));
+    uint32_t* counters = (uint32_t*)ctx->d_b3.ptr;
+    CU(cudaMemsetAsync(counters, 0, 64, s));
+    st_classify_kernel<<<grid1d(dev, m, 128), 128, 0, s>>>((const uint8_t*)sp->keys[sp->cur].ptr, n, dk, dlen, m, lb, kind, del_flag, ins_at, ins_flag,
+                                                           app_size, counters);
+    RC(scan_sizes(ctx, app_size, app_off, m));
+    RC(st_scan_u32(ctx, ins_flag, ins_index, m));
+    uint32_t hc[4] = {0, 0, 0, 0};
+    uint64_t app_bytes = 0;
+    CU(cudaMemcpyAsync(hc, counters, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&app_bytes, app_off + m, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    ctx->stats.launches += 5;
+    if (hc[2]) return PHANT_GPU_E_INVALID; // the same key twice in one update
+    const uint32_t n_ins = hc[0], n_del = hc[1];
+    // ---- values into the arena (grown with contents preserved; compaction is a rebuild-time concern) ----
+    if (sp->arena_used + app_bytes + 64 > sp->arena.cap) {
+        DevBuf bigger;
+        RC(bigger.reserve(ctx, (sp->arena_used + app_bytes) * 2 + (1 << 20)));
+        if (sp->arena_used) CU(cudaMemcpyAsync(bigger.ptr, sp->arena.ptr, sp->arena_used, cudaMemcpyDeviceToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        sp->arena.release();
+        sp->arena = bigger;
+    }
+    SRec* recs_cur = (SRec*)sp->recs[sp->cur].ptr;
+    st_append_kernel<<<grid1d(dev, m, 256, 32), 256, 0, s>>>(dv, dvoff, dlen, kind, lb, app_off, m, sp->arena_used, (uint8_t*)sp->arena.ptr, recs_cur, drec);
+    sp->arena_used += app_bytes;
+    ctx->stats.launches++;
+    // ---- merge (skipped for pure value updates) ----
+    const uint32_t new_n = n - n_del + n_ins;
+    if (n_ins || n_del) {
+        const int nxt = 1 - sp->cur;
+        RC(sp->keys[nxt].reserve(ctx, 32ull * new_n + 64));
+        RC(sp->recs[nxt].reserve(ctx, 16ull * new_n + 64));
+        st_keep_kernel<<<grid1d(dev, n + 1, 256), 256, 0, s>>>(del_flag, n, keep);
+        RC(st_scan_u32(ctx, keep, Kscan, n + 1));
+        RC(st_scan_u32(ctx, ins_at, Iscan, n + 2));
+        if (n)
+            st_merge_table_kernel<<<grid1d(dev, n, 256), 256, 0, s>>>((const uint8_t*)sp->keys[sp->cur].ptr, recs_cur, n, del_flag, Kscan, Iscan,
+                                                                     (uint8_t*)sp->keys[nxt].ptr, (SRec*)sp->recs[nxt].ptr);
+        st_merge_dirty_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(dk, drec, kind, lb, ins_index, m, n, Kscan, (uint8_t*)sp->keys[nxt].ptr,
+                                                                 (SRec*)sp->recs[nxt].ptr);
+        ctx->stats.launches += 5;
+        sp->cur = nxt;
+        sp->n = new_n;
+    }
+    sp->updates++;
+    if (new_n == 0) {
+        sp->L = 0;
+        memcpy(sp->root, EMPTY_ROOT_H, 32);
+        memcpy(out_root, sp->root, 32);
+        return PHANT_GPU_OK;
+    }
+    // ---- which part of the trie to re-hash ----
+    const uint32_t Lt = st_target_L(new_n);
+    int rc;
+    if (Lt > sp->L || Lt + 1 < sp->L || n == 0) {
+        rc = st_set_L_and_rebuild_all(t, Lt);      // the table grew / shrank past a bucket-size bound: new dense depth
+    } else {
+        uint32_t* first = ins_flag;                 // (classification scratch is free again)
+        uint32_t* fpos = ins_index;
+        uint32_t* list = lb;
+        st_bucket_flag_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(dk, m, sp->L, bucket, first);
+        CU(cudaMemsetAsync(first + m, 0, 4, s));
+        RC(st_scan_u32(ctx, first, fpos, m + 1));
+        st_compact_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(bucket, first, fpos, m, list);
+        uint32_t nb = 0;
+        CU(cudaMemcpyAsync(&nb, fpos + m, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        ctx->stats.launches += 3;
+        rc = st_rebuild(t, list, nb, false);
+        if (rc == 1) rc = st_set_L_and_rebuild_all(t, sp->L - 1); // a dense node lost all but one child: fewer dense levels
+    }
+    if (rc) return rc;
+    memcpy(out_root, sp->root, 32);
+    ctx->stats.d2h_bytes += 36;
+    return PHANT_GPU_OK;
+}
+
+} // namespace
+
 extern "C" int phant_gpu_trie_open(phant_gpu_ctx* ctx, const phant_gpu_trie_desc* desc, phant_gpu_trie** out)
 {
     if (!ctx || !desc || !out) return PHANT_GPU_E_INVALID;
     *out = nullptr;
+    if (desc->kind == 1) { // sparse resident secure trie, initially empty
+        CU(cudaSetDevice(ctx->device));
+        phant_gpu_trie* t = new (std::nothrow) phant_gpu_trie();
+        SparseTrie* sp = new (std::nothrow) SparseTrie();
+        if (!t || !sp) { delete t; delete sp; return PHANT_GPU_E_OOM; }
+        t->ctx = ctx; t->kind = 1; t->depth = 0; t->sp = sp;
+        memcpy(sp->root, EMPTY_ROOT_H, 32);
+        *out = t;
+        return PHANT_GPU_OK;
+    }
     if (desc->kind != 0 || desc->depth < 1 || desc->depth > 7) return PHANT_GPU_E_INVALID;
     CU(cudaSetDevice(ctx->device));
     phant_gpu_trie* t = new (std::nothrow) phant_gpu_trie();
@@ -1403,6 +1953,7 @@ extern "C" int phant_gpu_trie_root(phant_gpu_trie* t, uint8_t out_root[32])
 {
     if (!t || !out_root) return PHANT_GPU_E_INVALID;
     phant_gpu_ctx* ctx = t->ctx;
+    if (t->kind == 1) { memcpy(out_root, t->sp->root, 32); return PHANT_GPU_OK; }
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(out_root, t->level[0], 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1415,6 +1966,7 @@ extern "C" int phant_gpu_trie_update(phant_gpu_trie* t, const uint8_t* keys32, c
     if (!t || !out_root) return PHANT_GPU_E_INVALID;
     phant_gpu_ctx* ctx = t->ctx;
     CU(cudaSetDevice(ctx->device));
+    if (t->kind == 1) return strie_update(t, keys32, leaf_vals, val_off, n_dirty, out_root);
     cudaStream_t s = ctx->stream;
     if (n_dirty == 0) return phant_gpu_trie_root(t, out_root);
     if (!keys32 || !val_off || n_dirty >= (1ull << 28)) return PHANT_GPU_E_INVALID;
@@ -1564,5 +2116,11 @@ extern "C" void phant_gpu_trie_close(phant_gpu_trie* t)
     cudaStreamSynchronize(t->ctx->stream);
     t->store.release();
     t->work.release();
+    if (t->sp) {
+        SparseTrie* sp = t->sp;
+        for (DevBuf* b : {&sp->keys[0], &sp->keys[1], &sp->recs[0], &sp->recs[1], &sp->arena, &sp->top, &sp->present, &sp->sa, &sp->sb, &sp->sc, &sp->sd,
+                          &sp->se, &sp->sf, &sp->sg, &sp->sh, &sp->sroots, &sp->ssort}) b->release();
+        delete sp;
+    }
     delete t;
 }
