@@ -333,6 +333,58 @@ def bench_c4(ctx, gpu, torch, dev, steps):
             "parity": "tests/test_gpu_trie.py::test_resident_trie_full_size (root == oracle full recompute)", "scaling": "replicas only"}
 
 
+def bench_c4_sparse(ctx, gpu, torch, dev, steps):
+    """The same config on a REAL state shape (U kind 1): a sparse secure trie of 16^6 random 32-byte keys with 78-byte
+    account bodies resident on the device (sorted key table + values + a dense top of 5 nibble levels); every step upserts
+    100,000 existing keys with new values from pinned host memory and reads the root back; then one mixed step (50k inserts +
+    50k deletes, which re-merges the table).  Replicas only at N > 1."""
+    import numpy as np
+    n_keys = int(os.environ.get("PHANT_BENCH_SPARSE_KEYS", str(16 ** 6)))
+    n_dirty = 100_000
+    ctx.set_flags(0)
+    rng = np.random.default_rng(6)
+    keys = rng.integers(0, 256, (n_keys, 32), dtype=np.uint8)
+    vals = rng.integers(0, 256, n_keys * 78, dtype=np.uint8)
+    voff = (np.arange(n_keys + 1, dtype=np.uint64) * 78).astype(np.uint32)
+    trie = ctx.trie_open(0, kind=1)
+    t0 = time.perf_counter()
+    root0 = trie.update(np.ascontiguousarray(keys.reshape(-1)), vals, voff, n_keys)
+    build_s = time.perf_counter() - t0
+    del vals
+    sets = []
+    for _ in range(3):
+        pick = rng.choice(n_keys, size=n_dirty, replace=False)
+        k = torch.from_numpy(np.ascontiguousarray(keys[pick].reshape(-1))).pin_memory()
+        v = torch.from_numpy(rng.integers(0, 256, n_dirty * 78, dtype=np.uint8)).pin_memory()
+        o = torch.from_numpy((np.arange(n_dirty + 1) * 78).astype(np.uint32)).pin_memory()
+        sets.append((k, v, o))
+    trie.update(*sets[0], n_dirty)
+    ctx.reset_stats()
+    times = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        trie.update(*sets[i % 3], n_dirty)
+        times.append(time.perf_counter() - t0)
+    st = ctx.stats()
+    # mixed: 50k fresh keys in, 50k old keys out
+    pick = rng.choice(n_keys, size=n_dirty // 2, replace=False)
+    mk = np.concatenate([rng.integers(0, 256, (n_dirty // 2, 32), dtype=np.uint8), keys[pick]])
+    mv = rng.integers(0, 256, (n_dirty // 2) * 78, dtype=np.uint8)
+    mo = np.concatenate([np.arange(n_dirty // 2 + 1) * 78, np.full(n_dirty // 2, (n_dirty // 2) * 78)]).astype(np.uint32)
+    t0 = time.perf_counter()
+    trie.update(np.ascontiguousarray(mk.reshape(-1)), mv, mo, n_dirty)
+    mixed_ms = 1e3 * (time.perf_counter() - t0)
+    trie.close()
+    ms = sorted(1e3 * x for x in times)
+    return {"workload": f"sparse resident secure trie, {n_keys} random 32-byte keys x 78-byte values; {n_dirty} value upserts per step (host-pointer ABI, root read back)",
+            "steps": steps, "ms_per_update": {"min": ms[0], "median": ms[len(ms) // 2], "max": ms[-1]},
+            "launches_per_update": st["launches"] / steps, "keccak_ms_per_update": st["keccak_ms"] / steps,
+            "keccak_msgs_per_update": st["keccak_msgs"] / steps, "mixed_insert_delete_update_ms": mixed_ms, "initial_build_s": build_s,
+            "full_rebuild_equiv": "the initial build re-hashes every node: what StateDB.root() costs without a resident structure",
+            "parity": "tests/test_gpu_trie.py::test_sparse_resident_trie_* (root == oracle.mptize after every update), fixture post roots by update",
+            "scaling": "replicas only"}
+
+
 def bench_c5(ctx, gpu, torch, dev, rank, world, steps, barrier):
     """BASELINE configs[4]: 1000 blocks x 300 tx, deduplicated witness per block, BLOCKS sharded over the ranks; per-block
     verdict = no rejected proof; one all-reduce over u32 reject_count[1000] (phant_gpu_block_reject_counts)."""
@@ -546,6 +598,7 @@ def run_gpu(args, rank, world, local_rank):
         if rank == 0:
             extras["keccak_by_size"] = bench_mhs(ctx, gpu, torch, dev)
             extras["c4"] = bench_c4(ctx, gpu, torch, dev, max(5, min(args.steps, 10)))
+            extras["c4_sparse"] = bench_c4_sparse(ctx, gpu, torch, dev, max(5, min(args.steps, 10)))
         barrier()
     clocks = sampler.stop() if rank == 0 else None
 

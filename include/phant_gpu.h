@@ -192,14 +192,22 @@ int phant_gpu_logs_bloom(phant_gpu_ctx* ctx, const uint8_t* items, const uint64_
 int phant_gpu_ecrecover_batch(phant_gpu_ctx* ctx, const uint8_t* hashes32, const uint8_t* sigs65, uint64_t n,
                               uint8_t* pubkeys65, uint8_t* addresses20, uint8_t* ok);
 
-/* U -- resident trie + dirty-frontier root recompute (BASELINE.json "state-root recompute").
- * Round-1 shape: a complete 16-ary trie with `depth` branch levels (16^depth leaves) whose untouched
- * leaf hashes come from the synthetic PRNG; update rewrites n_dirty leaves (distinct leaf positions)
- * and re-hashes only the dirty frontier level by level.  Hook: StateDB.root() after a block. */
+/* U -- resident trie + dirty-frontier root recompute (BASELINE.json "state-root recompute").  Hook: StateDB.root() after
+ * a block (src/blockchain/blockchain.zig:83-85).  Two kinds:
+ *   kind 0  a complete 16-ary trie with `depth` branch levels (16^depth leaves) whose untouched leaf hashes come from the
+ *           synthetic PRNG (the benchmark shape); update rewrites n_dirty leaves at DISTINCT leaf positions (a collision is
+ *           refused with PHANT_GPU_E_INVALID and leaves the trie untouched) and re-hashes only the dirty frontier;
+ *   kind 1  a SPARSE secure trie over arbitrary 32-byte keys (keccak(address) / keccak(slot)) with arbitrary values, initially
+ *           empty: phant_gpu_trie_update is an UPSERT of (key, value) pairs in any order, an empty value DELETES the key
+ *           (absent keys are ignored), the same key twice in one call is PHANT_GPU_E_INVALID.  Resident on the device: the
+ *           sorted key table, the values, and the references of a dense top of L = floor(log16(n / 16)) nibble levels; an
+ *           update re-builds only the buckets (keys sharing an L-nibble prefix) that hold a dirty key -- with all of mptize's
+ *           rules: extensions, embedded nodes -- and re-hashes the dirty part of the dense levels.  Host pointers only.
+ *           The root always equals mptize over the current key set (src/mpt/mpt.zig:38-45). */
 typedef struct phant_gpu_trie phant_gpu_trie;
 typedef struct {
-    uint32_t kind;  /* 0 = complete synthetic trie */
-    uint32_t depth; /* branch levels */
+    uint32_t kind;  /* 0 = complete synthetic trie, 1 = sparse secure trie */
+    uint32_t depth; /* kind 0: branch levels; kind 1: ignored */
     uint64_t seed;
     uint64_t reserved[4];
 } phant_gpu_trie_desc;

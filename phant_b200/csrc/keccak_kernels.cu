@@ -367,6 +367,7 @@ keccak_regroup_kernel(const uint64_t* __restrict__ off, uint64_t n, uint64_t chu
             for (int w = 0; w < CLS_WARPS; ++w) t += wcnt[w][threadIdx.x];
             base[threadIdx.x] += t;
         }
+        __syncthreads(); // wcnt is cleared at the top of the next tile: not before the sums above have been taken
     }
 }
 

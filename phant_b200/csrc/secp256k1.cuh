@@ -66,20 +66,87 @@ __device__ __forceinline__ bool geq(const u256& a, const u256& b)
 }
 __device__ __forceinline__ uint64_t add_raw(u256& r, const u256& a, const u256& b)
 {
+#if defined(__CUDA_ARCH__)
+    uint64_t c;
+    asm("{\n\t"
+        "add.cc.u64 %0, %5, %9;\n\t"
+        "addc.cc.u64 %1, %6, %10;\n\t"
+        "addc.cc.u64 %2, %7, %11;\n\t"
+        "addc.cc.u64 %3, %8, %12;\n\t"
+        "addc.u64 %4, 0, 0;\n\t"
+        "}"
+        : "=&l"(r.v[0]), "=&l"(r.v[1]), "=&l"(r.v[2]), "=&l"(r.v[3]), "=&l"(c)
+        : "l"(a.v[0]), "l"(a.v[1]), "l"(a.v[2]), "l"(a.v[3]), "l"(b.v[0]), "l"(b.v[1]), "l"(b.v[2]), "l"(b.v[3]));
+    return c;
+#else
     uint64_t c = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.v[i] = adc(a.v[i], b.v[i], c);
     return c;
+#endif
 }
 __device__ __forceinline__ uint64_t sub_raw(u256& r, const u256& a, const u256& b)
 {
+#if defined(__CUDA_ARCH__)
+    uint64_t bw;
+    asm("{\n\t"
+        "sub.cc.u64 %0, %5, %9;\n\t"
+        "subc.cc.u64 %1, %6, %10;\n\t"
+        "subc.cc.u64 %2, %7, %11;\n\t"
+        "subc.cc.u64 %3, %8, %12;\n\t"
+        "subc.u64 %4, 0, 0;\n\t"
+        "}"
+        : "=&l"(r.v[0]), "=&l"(r.v[1]), "=&l"(r.v[2]), "=&l"(r.v[3]), "=&l"(bw)
+        : "l"(a.v[0]), "l"(a.v[1]), "l"(a.v[2]), "l"(a.v[3]), "l"(b.v[0]), "l"(b.v[1]), "l"(b.v[2]), "l"(b.v[3]));
+    return bw & 1; // subc of 0 - 0 - borrow: all ones when a borrow came in
+#else
     uint64_t bw = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.v[i] = sbb(a.v[i], b.v[i], bw);
     return bw;
+#endif
 }
+// 256 x 256 -> 512 bits.  Device: one asm block per row so that the hardware carry flag links the 64-bit multiply-adds
+// (mad.lo.cc / madc.hi.cc); written in C the carries become compare + select pairs, about a third of all instructions of
+// the recovery kernel.  Host (tests/hostcheck): the portable statement of the same schoolbook product.
 __device__ __forceinline__ void mul_wide(uint64_t (&t)[8], const u256& a, const u256& b)
 {
+#if defined(__CUDA_ARCH__)
+    const uint64_t b0 = b.v[0], b1 = b.v[1], b2 = b.v[2], b3 = b.v[3];
+    {   // row 0: t[0..4] = a0 * b
+        const uint64_t x = a.v[0];
+        asm("{\n\t"
+            "mul.lo.u64 %0, %5, %6;\n\t"
+            "mul.hi.u64 %1, %5, %6;\n\t"
+            "mul.hi.u64 %2, %5, %7;\n\t"
+            "mul.hi.u64 %3, %5, %8;\n\t"
+            "mul.hi.u64 %4, %5, %9;\n\t"
+            "mad.lo.cc.u64 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u64 %2, %5, %8, %2;\n\t"
+            "madc.lo.cc.u64 %3, %5, %9, %3;\n\t"
+            "addc.u64 %4, %4, 0;\n\t"
+            "}"
+            : "=&l"(t[0]), "=&l"(t[1]), "=&l"(t[2]), "=&l"(t[3]), "=&l"(t[4])
+            : "l"(x), "l"(b0), "l"(b1), "l"(b2), "l"(b3));
+    }
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { // row i: t[i..i+4] += a_i * b  (t[i+4] is created by this row)
+        const uint64_t x = a.v[i];
+        asm("{\n\t"
+            "mad.lo.cc.u64 %0, %5, %6, %0;\n\t"
+            "madc.lo.cc.u64 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u64 %2, %5, %8, %2;\n\t"
+            "madc.lo.cc.u64 %3, %5, %9, %3;\n\t"
+            "addc.u64 %4, 0, 0;\n\t"
+            "mad.hi.cc.u64 %1, %5, %6, %1;\n\t"
+            "madc.hi.cc.u64 %2, %5, %7, %2;\n\t"
+            "madc.hi.cc.u64 %3, %5, %8, %3;\n\t"
+            "madc.hi.u64 %4, %5, %9, %4;\n\t"
+            "}"
+            : "+l"(t[i]), "+l"(t[i + 1]), "+l"(t[i + 2]), "+l"(t[i + 3]), "=&l"(t[i + 4])
+            : "l"(x), "l"(b0), "l"(b1), "l"(b2), "l"(b3));
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 8; ++i) t[i] = 0;
 #pragma unroll
@@ -89,6 +156,7 @@ __device__ __forceinline__ void mul_wide(uint64_t (&t)[8], const u256& a, const 
         for (int j = 0; j < 4; ++j) t[i + j] = mac(a.v[i], b.v[j], t[i + j], carry, carry);
         t[i + 4] = carry;
     }
+#endif
 }
 __device__ __forceinline__ u256 from_be(const uint8_t* b)
 {
@@ -123,26 +191,58 @@ __device__ __forceinline__ void fp_norm(u256& r) // r < 2^256 -> r mod p
 __device__ __forceinline__ u256 fp_add(const u256& a, const u256& b)
 {
     u256 r;
-    uint64_t c = add_raw(r, a, b);
-    if (c) { // r + 2^256 == r + C (mod p); cannot carry again: a, b < p
-        uint64_t k = 0;
-        r.v[0] = adc(r.v[0], FP_C, k); r.v[1] = adc(r.v[1], 0, k); r.v[2] = adc(r.v[2], 0, k); r.v[3] = adc(r.v[3], 0, k);
-    }
+    const uint64_t c = add_raw(r, a, b);
+    // r + 2^256 == r + C (mod p); cannot carry again: a, b < p.  Branch-free: add c * C (c is 0 or 1)
+    const u256 k{{c ? FP_C : 0, 0, 0, 0}};
+    add_raw(r, r, k);
     fp_norm(r);
     return r;
 }
 __device__ __forceinline__ u256 fp_sub(const u256& a, const u256& b)
 {
     u256 r;
-    if (sub_raw(r, a, b)) { // went below zero: add p == subtract C (mod 2^256)
-        uint64_t bw = 0;
-        r.v[0] = sbb(r.v[0], FP_C, bw); r.v[1] = sbb(r.v[1], 0, bw); r.v[2] = sbb(r.v[2], 0, bw); r.v[3] = sbb(r.v[3], 0, bw);
-    }
+    const uint64_t bw = sub_raw(r, a, b);
+    // went below zero: add p == subtract C (mod 2^256)
+    const u256 k{{bw ? FP_C : 0, 0, 0, 0}};
+    sub_raw(r, r, k);
     return r;
 }
 __device__ __forceinline__ u256 fp_neg(const u256& a) { return is_zero(a) ? a : fp_sub(u256{{0, 0, 0, 0}}, a); }
 __device__ __forceinline__ u256 fp_reduce(const uint64_t (&t)[8])
 {
+#if defined(__CUDA_ARCH__)
+    // lo + hi * C (C < 2^33): five limbs r0..r4 with r4 < 2^34, then r4 * C folded in once more; k = the last carry
+    uint64_t r0, r1, r2, r3, r4, k;
+    u256 o;
+    asm("{\n\t"
+        "mad.lo.cc.u64 %0, %9, %13, %5;\n\t"
+        "madc.lo.cc.u64 %1, %10, %13, %6;\n\t"
+        "madc.lo.cc.u64 %2, %11, %13, %7;\n\t"
+        "madc.lo.cc.u64 %3, %12, %13, %8;\n\t"
+        "addc.u64 %4, 0, 0;\n\t"
+        "mad.hi.cc.u64 %1, %9, %13, %1;\n\t"
+        "madc.hi.cc.u64 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u64 %3, %11, %13, %3;\n\t"
+        "madc.hi.u64 %4, %12, %13, %4;\n\t"
+        "}"
+        : "=&l"(r0), "=&l"(r1), "=&l"(r2), "=&l"(r3), "=&l"(r4)
+        : "l"(t[0]), "l"(t[1]), "l"(t[2]), "l"(t[3]), "l"(t[4]), "l"(t[5]), "l"(t[6]), "l"(t[7]), "l"(FP_C));
+    asm("{\n\t"
+        ".reg .u64 hi;\n\t"
+        "mul.hi.u64 hi, %9, %10;\n\t"
+        "mad.lo.cc.u64 %0, %9, %10, %5;\n\t"
+        "addc.cc.u64 %1, %6, hi;\n\t"
+        "addc.cc.u64 %2, %7, 0;\n\t"
+        "addc.cc.u64 %3, %8, 0;\n\t"
+        "addc.u64 %4, 0, 0;\n\t"
+        "}"
+        : "=&l"(o.v[0]), "=&l"(o.v[1]), "=&l"(o.v[2]), "=&l"(o.v[3]), "=&l"(k)
+        : "l"(r0), "l"(r1), "l"(r2), "l"(r3), "l"(r4), "l"(FP_C));
+    const u256 kc{{k ? FP_C : 0, 0, 0, 0}}; // wrapped once more: the value left is tiny, adding C cannot carry
+    add_raw(o, o, kc);
+    fp_norm(o);
+    return o;
+#else
     // lo + hi * C: hi * C is 4 limbs x 33 bits
     uint64_t r[5], carry = 0;
 #pragma unroll
@@ -163,6 +263,7 @@ __device__ __forceinline__ u256 fp_reduce(const uint64_t (&t)[8])
     }
     fp_norm(o);
     return o;
+#endif
 }
 __device__ __forceinline__ u256 fp_mul(const u256& a, const u256& b)
 {
@@ -172,20 +273,50 @@ __device__ __forceinline__ u256 fp_mul(const u256& a, const u256& b)
 }
 __device__ __forceinline__ u256 fp_sqr(const u256& a) { return fp_mul(a, a); }
 __device__ __forceinline__ u256 fp_dbl(const u256& a) { return fp_add(a, a); }
-// a^e for a compile-time-known exponent held in four words (bits scanned high to low; the branch is warp-uniform)
-__device__ __noinline__ u256 fp_pow(const u256& a, uint64_t e3, uint64_t e2, uint64_t e1, uint64_t e0)
+// a^(2^k) (k >= 1)
+__device__ __forceinline__ u256 fp_sqr_n(u256 a, int k)
 {
-    const uint64_t e[4] = {e0, e1, e2, e3};
-    u256 acc{{1, 0, 0, 0}};
 #pragma unroll 1
-    for (int i = 255; i >= 0; --i) {
-        acc = fp_sqr(acc);
-        if ((e[i >> 6] >> (i & 63)) & 1) acc = fp_mul(acc, a);
-    }
-    return acc;
+    for (int i = 0; i < k; ++i) a = fp_sqr(a);
+    return a;
 }
-__device__ __forceinline__ u256 fp_inv(const u256& a) { return fp_pow(a, ~0ull, ~0ull, ~0ull, 0xFFFFFFFEFFFFFC2Dull); }          // a^(p-2)
-__device__ __forceinline__ u256 fp_sqrt_candidate(const u256& a) { return fp_pow(a, 0x3FFFFFFFFFFFFFFFull, ~0ull, ~0ull, 0xFFFFFFFFBFFFFF0Cull); } // a^((p+1)/4)
+// Both exponents p - 2 and (p + 1) / 4 start with a run of 223 ones, a zero, then 22 ones: build a^(2^223 - 1) once with the
+// classic ladder of runs (x2, x3, x6, x9, x11, x22, x44, x88, x176, x220, x223: 11 multiplications) instead of one
+// multiplication per exponent bit -- 255 squarings + 15 multiplications for the inverse, 253 + 13 for the square root.
+struct FpRuns { u256 x2, x22, x223; };
+__device__ __noinline__ FpRuns fp_runs(const u256& a)
+{
+    FpRuns r;
+    r.x2 = fp_mul(fp_sqr(a), a);
+    const u256 x3 = fp_mul(fp_sqr(r.x2), a);
+    const u256 x6 = fp_mul(fp_sqr_n(x3, 3), x3);
+    const u256 x9 = fp_mul(fp_sqr_n(x6, 3), x3);
+    const u256 x11 = fp_mul(fp_sqr_n(x9, 2), r.x2);
+    r.x22 = fp_mul(fp_sqr_n(x11, 11), x11);
+    const u256 x44 = fp_mul(fp_sqr_n(r.x22, 22), r.x22);
+    const u256 x88 = fp_mul(fp_sqr_n(x44, 44), x44);
+    const u256 x176 = fp_mul(fp_sqr_n(x88, 88), x88);
+    const u256 x220 = fp_mul(fp_sqr_n(x176, 44), x44);
+    r.x223 = fp_mul(fp_sqr_n(x220, 3), x3);
+    return r;
+}
+// a^(p-2): p - 2 = 1^223 0 1^22 0000 1 0 1 1 0 1 (binary)
+__device__ __forceinline__ u256 fp_inv(const u256& a)
+{
+    const FpRuns r = fp_runs(a);
+    u256 t = fp_mul(fp_sqr_n(r.x223, 23), r.x22);
+    t = fp_mul(fp_sqr_n(t, 5), a);
+    t = fp_mul(fp_sqr_n(t, 3), r.x2);
+    return fp_mul(fp_sqr_n(t, 2), a);
+}
+// a^((p+1)/4): (p + 1) / 4 = 1^223 0 1^22 0000 1 1 00 (binary)
+__device__ __forceinline__ u256 fp_sqrt_candidate(const u256& a)
+{
+    const FpRuns r = fp_runs(a);
+    u256 t = fp_mul(fp_sqr_n(r.x223, 23), r.x22);
+    t = fp_mul(fp_sqr_n(t, 6), r.x2);
+    return fp_sqr_n(t, 2);
+}
 
 // ---- scalars mod n, n = 2^256 - K, K = 0x1_4551231950B75FC4_402DA1732FC9BEBF ----
 __device__ __forceinline__ u256 sc_n() { return u256{{0xBFD25E8CD0364141ull, 0xBAAEDCE6AF48A03Bull, 0xFFFFFFFFFFFFFFFEull, ~0ull}}; }
@@ -221,12 +352,30 @@ __device__ __forceinline__ u256 sc_neg(const u256& a)
     sub_raw(r, sc_n(), a);
     return r;
 }
-__device__ __noinline__ u256 sc_inv(const u256& a) // a^(n-2), n prime
+__device__ __forceinline__ u256 sc_sqr_n(u256 a, int k)
 {
-    const uint64_t e[4] = {0xBFD25E8CD036413Full, 0xBAAEDCE6AF48A03Bull, 0xFFFFFFFFFFFFFFFEull, ~0ull};
-    u256 acc{{1, 0, 0, 0}};
 #pragma unroll 1
-    for (int i = 255; i >= 0; --i) {
+    for (int i = 0; i < k; ++i) a = sc_mul(a, a);
+    return a;
+}
+// a^(n-2), n prime.  The top half of n - 2 is 127 ones and a zero: a^(2^127 - 1) comes from a ladder of runs (10
+// multiplications); the bottom 128 bits are taken one by one (64 of them set): 255 squarings + 74 multiplications.
+__device__ __noinline__ u256 sc_inv(const u256& a)
+{
+    const u256 x2 = sc_mul(sc_mul(a, a), a);
+    const u256 x3 = sc_mul(sc_mul(x2, x2), a);
+    const u256 x6 = sc_mul(sc_sqr_n(x3, 3), x3);
+    const u256 x12 = sc_mul(sc_sqr_n(x6, 6), x6);
+    const u256 x24 = sc_mul(sc_sqr_n(x12, 12), x12);
+    const u256 x48 = sc_mul(sc_sqr_n(x24, 24), x24);
+    const u256 x96 = sc_mul(sc_sqr_n(x48, 48), x48);
+    const u256 x120 = sc_mul(sc_sqr_n(x96, 24), x24);
+    const u256 x126 = sc_mul(sc_sqr_n(x120, 6), x6);
+    u256 acc = sc_mul(sc_mul(x126, x126), a); // x127
+    acc = sc_mul(acc, acc);                  // the zero bit
+    const uint64_t e[2] = {0xBFD25E8CD036413Full, 0xBAAEDCE6AF48A03Bull};
+#pragma unroll 1
+    for (int i = 127; i >= 0; --i) {
         acc = sc_mul(acc, acc);
         if ((e[i >> 6] >> (i & 63)) & 1) acc = sc_mul(acc, a);
     }

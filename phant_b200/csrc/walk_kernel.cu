@@ -46,14 +46,14 @@ walk_kernel(const Bag bag, uint64_t n_proofs, const uint8_t* __restrict__ nodes,
 
 } // namespace
 
-// tuning knob (development): PHANT_WALK_MINB = 8 | 10 | 12 | 16; the default is the measured best
+// tuning knob (development): PHANT_WALK_MINB = 6 | 8 | 10 | 12 | 16; the default is the measured best
 static int walk_minb()
 {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PHANT_WALK_MINB");
         v = e ? atoi(e) : 8;
-        if (v != 10 && v != 12 && v != 16) v = 8;
+        if (v != 6 && v != 10 && v != 12 && v != 16) v = 8;
     }
     return v;
 }
@@ -69,6 +69,7 @@ cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uin
     if (blocks > cap) blocks = cap;
 #define PHANT_WALK_ARGS Bag{nullptr, 0}, n_proofs, nodes, node_off, node_index, proof_first, keys32, roots32, n_roots, digests, summary, bitmap, status, val_off, val_len
     switch (walk_minb()) {
+    case 6: walk_kernel<false, 6><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;
     case 10: walk_kernel<false, 10><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;
     case 12: walk_kernel<false, 12><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;
     case 16: walk_kernel<false, 16><<<(unsigned)blocks, 128, 0, s>>>(PHANT_WALK_ARGS); break;

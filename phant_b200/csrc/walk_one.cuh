@@ -134,27 +134,52 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
     uint32_t cur_len = 0;
     bool embedded = false;
 
+    // Chain modes: node i+1's index, offsets, summary and digest do not depend on what node i holds, so they are requested
+    // one node AHEAD -- while this node's digest is compared and its child hash fetched, the next node's metadata is already
+    // in flight; the only load left on the dependent path of a simple branch is the 32-byte child hash itself.
+    struct Meta { uint64_t ni, o0, o1; uint32_t sm; uint32_t dg[8]; };
+    Meta nxt{};
+    auto fetch = [&](uint64_t at, Meta& m) {
+        m.ni = node_index ? node_index[at] : at; // deduplicated witness: the chain holds node indices
+        m.o0 = node_off[m.ni];
+        m.o1 = node_off[m.ni + 1];
+        m.sm = summary ? summary[m.ni] : 0;
+        load32_aligned(digests + 32 * m.ni, m.dg);
+    };
+    if (!BAG) fetch(first, nxt);
+
     for (;;) {
         if (!embedded) {
             uint64_t ni;
+            uint32_t sm;
             if (BAG) {
                 const uint32_t f = bag_find(bag, digests, expect);
                 if (f == BAG_EMPTY) return ST_MISSING; // the witness does not contain the node this reference names
                 ni = f;
                 i = last - 1; // so that ++i below leaves i == last: every terminal test sees "last node"
+                const uint64_t o = node_off[ni];
+                const uint64_t l = node_off[ni + 1] - o;
+                if (l > 0xffffffffull) return ST_REJECT;
+                cur = nodes + o;
+                cur_len = (uint32_t)l;
+                sm = summary ? summary[ni] : 0;
             } else {
                 if (i == last) return ST_REJECT; // R3: a hash reference needs a node
-                ni = node_index ? node_index[i] : i; // deduplicated witness: the chain holds node indices
+                const Meta m = nxt;
+                if (i + 1 < last) fetch(i + 1, nxt);
+                ni = m.ni;
+                const uint64_t l = m.o1 - m.o0;
+                if (l > 0xffffffffull) return ST_REJECT;
+                cur = nodes + m.o0;
+                cur_len = (uint32_t)l;
+                uint32_t diff = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) diff |= m.dg[w] ^ expect[w];
+                if (diff) return ST_REJECT; // R1 (bag: the lookup compared it)
+                sm = m.sm;
             }
-            const uint64_t o = node_off[ni];
-            const uint64_t l = node_off[ni + 1] - o;
-            if (l > 0xffffffffull) return ST_REJECT;
-            cur = nodes + o;
-            cur_len = (uint32_t)l;
-            if (!BAG && !eq32_aligned(digests + 32 * ni, expect)) return ST_REJECT; // R1 (bag: the lookup compared it)
             // fast path: the hash kernel already proved this node a simple branch (canonical 17-item list, children
             // empty or 32-byte hashes, empty value) and left the child mask: no parse, one 32-byte fetch
-            const uint32_t sm = summary ? summary[ni] : 0;
             ++i;
             if ((sm & 3u) == 1u && pos < 64) {
                 const uint32_t nibble = (pos & 1) ? (key[pos >> 1] & 15u) : (key[pos >> 1] >> 4);

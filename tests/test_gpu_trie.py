@@ -341,7 +341,6 @@ def test_fixture_post_state_roots_by_updating_the_pre_state_trie(ctx, oracle, go
         changes.update({k: b"" for k in pre if k not in post})
         root = _apply(trie, state, changes) if changes else trie.root()
         assert root.hex() == t["post_root"], t["name"]
-        assert len(changes) < max(len(post), 2) or len(post) <= 4
         trie.close()
         done += 1
     assert done == 84

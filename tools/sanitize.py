@@ -10,7 +10,7 @@ from gpu_util import random_csr
 o = oracle_lib.get()
 ctx = gpu.Context(0)
 rng = np.random.default_rng(0)
-data, off = random_csr(rng, 5000)
+data, off = random_csr(rng, 5000)      # >= 4096 messages: the two-launch regrouping (keccak_class / keccak_regroup) runs
 out = np.zeros((5000, 32), np.uint8)
 for flags in (0, 1 << 4, 1 << 5, 1 << 6):
     ctx.set_flags(flags)
@@ -36,5 +36,30 @@ keys = rng.integers(0, 256, (200, 32), dtype=np.uint8); keys[:, 0] = pos >> 4; k
 v, vo = oracle_lib.csr([rng.integers(0, 256, 70, dtype=np.uint8).tobytes() for _ in range(200)], np.uint32)
 t.update(np.ascontiguousarray(keys.reshape(-1)), v, vo, 200)
 t.close()
+# U kind 1: sparse resident trie -- build past the first dense level, value updates, deletes
+t = ctx.trie_open(0, kind=1)
+state = {rng.integers(0, 256, 32, dtype=np.uint8).tobytes(): rng.integers(0, 256, 50, dtype=np.uint8).tobytes() for _ in range(900)}
+def apply(ch):
+    ks = list(ch)
+    v, vo = oracle_lib.csr([ch[k] for k in ks], np.uint32)
+    return t.update(np.frombuffer(b"".join(ks), np.uint8), v, vo, len(ks))
+assert apply(state) == o.mptize(sorted(state.items()))
+ch = {k: b"x" * 40 for k in list(state)[:50]}
+ch.update({k: b"" for k in list(state)[50:90]})
+for k, v in ch.items():
+    if v: state[k] = v
+    else: del state[k]
+assert apply(ch) == o.mptize(sorted(state.items()))
+t.close()
+# W: node-set witness, B: blooms, R: sender recovery
+nodes, node_off = oracle_lib.csr([b["nodes"][int(b["node_off"][j]):int(b["node_off"][j + 1])].tobytes() for j in range(b["n_nodes"])], np.uint64)
+st = np.zeros(n, np.uint8)
+ctx.verify_witness(len(node_off) - 1, nodes, node_off, n, b["keys32"], b["roots32"], n, None, st, None, None)
+items, ioff = random_csr(rng, 300, max_len=40, pad_front=0)
+blooms = np.zeros((4, 256), np.uint8)
+ctx.logs_bloom(items, ioff, (np.arange(300) % 4).astype(np.uint32), 300, 4, blooms)
+h = rng.integers(0, 256, 32 * 64, dtype=np.uint8); sg = rng.integers(0, 256, 65 * 64, dtype=np.uint8); sg[64::65] &= 1
+ok = np.zeros(64, np.uint8); addr = np.zeros((64, 20), np.uint8)
+ctx.ecrecover_batch(h, sg, 64, None, addr, ok)
 ctx.close()
 print("sanitize workload ok")
