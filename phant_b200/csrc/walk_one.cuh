@@ -68,18 +68,27 @@ __device__ __forceinline__ bool eq32_aligned(const uint8_t* a, const uint32_t (&
     for (int i = 0; i < 8; ++i) diff |= d[i] ^ e[i];
     return diff == 0;
 }
-// 32 bytes at any address (a hash inside a node): aligned 32-bit loads + one funnel shift per word
+// 32 bytes at any address (a hash inside a node): the 48-byte aligned window around them as THREE 128-bit loads, then a word
+// select and one funnel shift per word.  One proof per lane means every load instruction touches 32 different lines, so the
+// walk is bound by the NUMBER of load instructions, not by bytes: three wide loads instead of nine narrow ones.  The window
+// may reach 15 bytes before `a` and 16 bytes past `a + 32`; both stay inside the node buffer (16-byte aligned base, 16 bytes
+// of slack behind the last node: include/phant_gpu.h).
 __device__ __forceinline__ void load32(const uint8_t* a, uint32_t (&e)[8])
 {
     const uintptr_t p = (uintptr_t)a;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(p & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(p & 3) * 8;
-    uint32_t v[9];
+    const uint4* q = reinterpret_cast<const uint4*>(p & ~(uintptr_t)15);
+    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    const uint32_t v[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    const uint32_t w0 = (uint32_t)(p & 15) >> 2, sh = (uint32_t)(p & 3) * 8;
+    uint32_t u[9];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = w[i];
-    v[8] = sh ? w[8] : 0;
+    for (int i = 0; i < 9; ++i) { // u[i] = v[w0 + i], w0 in 0..3, without dynamic register indexing
+        const uint32_t a01 = (w0 & 1) ? v[i + 1] : v[i];
+        const uint32_t a23 = (w0 & 1) ? v[i + 3 < 12 ? i + 3 : 11] : v[i + 2 < 12 ? i + 2 : 11];
+        u[i] = (w0 & 2) ? a23 : a01;
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) e[i] = __funnelshift_r(v[i], v[i + 1], sh);
+    for (int i = 0; i < 8; ++i) e[i] = __funnelshift_r(u[i], u[i + 1], sh);
 }
 __device__ __forceinline__ bool eq32_const(const uint8_t* a, const uint32_t (&e)[8])
 {
@@ -122,6 +131,17 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
     voff = 0; vlen = 0;
     uint32_t expect[8];
     load32_aligned(root, expect);
+    // the key lives in registers (two 128-bit loads) instead of one byte load per trie level
+    uint32_t kw[8];
+    load32_aligned(key, kw);
+    auto key_nibble = [&](uint32_t q) -> uint32_t { // nibble q of the key, q < 64
+        const uint32_t wi = q >> 3;
+        const uint32_t a01 = (wi & 1) ? kw[1] : kw[0], a23 = (wi & 1) ? kw[3] : kw[2], a45 = (wi & 1) ? kw[5] : kw[4], a67 = (wi & 1) ? kw[7] : kw[6];
+        const uint32_t lo4 = (wi & 2) ? a23 : a01, hi4 = (wi & 2) ? a67 : a45;
+        const uint32_t w = (wi & 4) ? hi4 : lo4;
+        const uint32_t byte = (w >> (8 * ((q >> 1) & 3))) & 0xffu;
+        return (q & 1) ? (byte & 15u) : (byte >> 4);
+    };
     if (BAG) { // no chain: first/last only feed the "is this the last node" tests, which always pass
         first = 0;
         last = 1;
@@ -134,55 +154,30 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
     uint32_t cur_len = 0;
     bool embedded = false;
 
-    // Chain modes: node i+1's index, offsets, summary and digest do not depend on what node i holds, so they are requested
-    // one node AHEAD -- while this node's digest is compared and its child hash fetched, the next node's metadata is already
-    // in flight; the only load left on the dependent path of a simple branch is the 32-byte child hash itself.
-    struct Meta { uint64_t ni, o0, o1; uint32_t sm; uint32_t dg[8]; };
-    Meta nxt{};
-    auto fetch = [&](uint64_t at, Meta& m) {
-        m.ni = node_index ? node_index[at] : at; // deduplicated witness: the chain holds node indices
-        m.o0 = node_off[m.ni];
-        m.o1 = node_off[m.ni + 1];
-        m.sm = summary ? summary[m.ni] : 0;
-        load32_aligned(digests + 32 * m.ni, m.dg);
-    };
-    if (!BAG) fetch(first, nxt);
-
     for (;;) {
         if (!embedded) {
             uint64_t ni;
-            uint32_t sm;
             if (BAG) {
                 const uint32_t f = bag_find(bag, digests, expect);
                 if (f == BAG_EMPTY) return ST_MISSING; // the witness does not contain the node this reference names
                 ni = f;
                 i = last - 1; // so that ++i below leaves i == last: every terminal test sees "last node"
-                const uint64_t o = node_off[ni];
-                const uint64_t l = node_off[ni + 1] - o;
-                if (l > 0xffffffffull) return ST_REJECT;
-                cur = nodes + o;
-                cur_len = (uint32_t)l;
-                sm = summary ? summary[ni] : 0;
             } else {
                 if (i == last) return ST_REJECT; // R3: a hash reference needs a node
-                const Meta m = nxt;
-                if (i + 1 < last) fetch(i + 1, nxt);
-                ni = m.ni;
-                const uint64_t l = m.o1 - m.o0;
-                if (l > 0xffffffffull) return ST_REJECT;
-                cur = nodes + m.o0;
-                cur_len = (uint32_t)l;
-                uint32_t diff = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) diff |= m.dg[w] ^ expect[w];
-                if (diff) return ST_REJECT; // R1 (bag: the lookup compared it)
-                sm = m.sm;
+                ni = node_index ? node_index[i] : i; // deduplicated witness: the chain holds node indices
             }
+            const uint64_t o = node_off[ni];
+            const uint64_t l = node_off[ni + 1] - o;
+            if (l > 0xffffffffull) return ST_REJECT;
+            cur = nodes + o;
+            cur_len = (uint32_t)l;
+            if (!BAG && !eq32_aligned(digests + 32 * ni, expect)) return ST_REJECT; // R1 (bag: the lookup compared it)
             // fast path: the hash kernel already proved this node a simple branch (canonical 17-item list, children
             // empty or 32-byte hashes, empty value) and left the child mask: no parse, one 32-byte fetch
+            const uint32_t sm = summary ? summary[ni] : 0;
             ++i;
             if ((sm & 3u) == 1u && pos < 64) {
-                const uint32_t nibble = (pos & 1) ? (key[pos >> 1] & 15u) : (key[pos >> 1] >> 4);
+                const uint32_t nibble = key_nibble(pos);
                 ++pos;
                 const uint32_t mask = sm >> 8;
                 if (!((mask >> nibble) & 1u)) return i == last ? ST_ABSENT : ST_REJECT; // empty slot (R3)
@@ -198,7 +193,7 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
         const uint32_t pl = top.pay_len;
 
         // one pass over the items: remember item 0, item 1, the item at the key's nibble and item 16
-        const uint32_t want = pos < 64 ? ((pos & 1) ? (key[pos >> 1] & 15u) : (key[pos >> 1] >> 4)) : 16u;
+        const uint32_t want = pos < 64 ? key_nibble(pos) : 16u;
         Item it0{}, it1{}, itw{}, it16{};
         uint32_t off0 = 0, off1 = 0, offw = 0, off16 = 0;
         uint32_t cnt = 0, o = 0;
@@ -237,14 +232,28 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
             const uint32_t plen = 2 * (it0.pay_len - 1) + (flag & 1);
             if (plen > 64) return ST_REJECT;
             bool match = 64 - pos >= plen;
-            if (match) {
+            if ((flag & 2) && pos + plen != 64) match = false; // a leaf only proves presence when its path ends the key: nothing to compare otherwise
+            else if (match && (flag & 2) && plen >= 2 && (uint64_t)(hp + it0.pay_len - nodes) >= 48) {
+                // leaf whose path ends exactly at the key's end: its last plen/2 bytes must equal the key's last plen/2 bytes (and,
+                // for an odd path, the low nibble of hp[0] the nibble before them) -- one wide load instead of a byte loop
+                uint32_t tail[8];
+                load32(hp + it0.pay_len - 32, tail);
+                const uint32_t nb = plen >> 1; // whole bytes compared: key bytes [32 - nb, 32)
+                uint32_t diff = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const int first = 32 - (int)nb - 4 * w; // first compared byte inside word w (<= 0: whole word, >= 4: none)
+                    const uint32_t m = first <= 0 ? 0xffffffffu : (first >= 4 ? 0u : 0xffffffffu << (8 * first));
+                    diff |= (tail[w] ^ kw[w]) & m;
+                }
+                if ((flag & 1) && (hp[0] & 15u) != key_nibble(pos)) diff = 1;
+                match = diff == 0;
+            } else if (match) {
                 // path nibble j: odd flag -> nibble 0 is hp[0]&15, then bytes; even -> bytes from hp[1]
                 for (uint32_t j = 0; j < plen; ++j) {
                     const uint32_t q = j + 2 - (flag & 1); // nibble index inside hp (2 nibbles per byte)
                     const uint32_t pn = (q & 1) ? (hp[q >> 1] & 15u) : (hp[q >> 1] >> 4);
-                    const uint32_t kq = pos + j;
-                    const uint32_t kn = (kq & 1) ? (key[kq >> 1] & 15u) : (key[kq >> 1] >> 4);
-                    if (pn != kn) { match = false; break; }
+                    if (pn != key_nibble(pos + j)) { match = false; break; }
                 }
             }
             if (flag & 2) { // leaf

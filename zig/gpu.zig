@@ -105,6 +105,59 @@ pub const Gpu = struct {
             return error.GpuBackend;
     }
 
+    // ---- multi-GPU: one Gpu (context) per device, one worker thread each (src/main.zig:143-149) ----
+
+    /// One process driving several devices: rank i = gpus[i].  NCCL is loaded inside libphantgpu.so.
+    pub fn commInitLocal(gpus: []Gpu, arena: Allocator) Error!void {
+        const ctxs = try arena.alloc(?*c.phant_gpu_ctx, gpus.len);
+        for (gpus, 0..) |g, i| ctxs[i] = g.ctx;
+        if (c.phant_gpu_comm_init_local(@ptrCast(ctxs.ptr), @intCast(gpus.len)) != 0) return error.GpuBackend;
+    }
+
+    /// One process per device: rank 0 creates the id (phant_gpu_comm_get_unique_id) and hands it to the others.
+    pub fn commInit(self: *Gpu, id: *const [c.PHANT_GPU_COMM_ID_BYTES]u8, rank: i32, world: i32) Error!void {
+        if (c.phant_gpu_comm_init(self.ctx, id, rank, world) != 0) return error.GpuBackend;
+    }
+
+    /// verifyProofs for this rank's shard of a batch of n_global proofs (phant_gpu_shard_range); on return global_bitmap
+    /// (phant_gpu_sharded_bitmap_words(n_global, world) words) holds every rank's accept bits.
+    pub fn verifyProofsSharded(self: *Gpu, local: *const c.phant_gpu_proof_batch, n_global: u64, global_bitmap: []u64, status: ?[]u8) Error!void {
+        const st: ?[*]u8 = if (status) |s| s.ptr else null;
+        if (c.phant_gpu_verify_proofs_sharded(self.ctx, local, n_global, global_bitmap.ptr, st, null, null) != 0) return error.GpuBackend;
+    }
+
+    /// StateDB.root() across GPUs: `mine` = the accounts whose keccak(address) top nibble this rank owns
+    /// (phant_gpu_nibble_owner); every rank gets the same root.
+    pub fn stateRootSharded(self: *Gpu, mine: *const c.phant_gpu_accounts) Error!Hash32 {
+        var root: Hash32 = undefined;
+        if (c.phant_gpu_state_root_sharded(self.ctx, mine, &root) != 0) return error.GpuBackend;
+        return root;
+    }
+
+    // ---- resident state trie: StateDB.root() after a block costs the dirty accounts, not a rebuild ----
+
+    pub const ResidentTrie = struct {
+        t: *c.phant_gpu_trie,
+
+        /// kind 1: sparse secure trie, initially empty; feed it the genesis / snapshot accounts with one `apply`.
+        pub fn open(gpu: *Gpu) Error!ResidentTrie {
+            var desc = std.mem.zeroes(c.phant_gpu_trie_desc);
+            desc.kind = 1;
+            var t: ?*c.phant_gpu_trie = null;
+            if (c.phant_gpu_trie_open(gpu.ctx, &desc, &t) != 0) return error.GpuBackend;
+            return .{ .t = t.? };
+        }
+        /// upsert (keccak(address) -> rlp(account)); an empty value deletes the account.  Returns the new state root.
+        pub fn apply(self: *ResidentTrie, keys32: []const u8, vals: []const u8, val_off: []const u32) Error!Hash32 {
+            var root: Hash32 = undefined;
+            if (c.phant_gpu_trie_update(self.t, keys32.ptr, vals.ptr, val_off.ptr, val_off.len - 1, &root) != 0) return error.GpuBackend;
+            return root;
+        }
+        pub fn close(self: *ResidentTrie) void {
+            c.phant_gpu_trie_close(self.t);
+        }
+    };
+
     /// Receipt.calculateLogsBloom (src/types/receipt.zig:37-48) for all receipts of a block.
     pub fn logsBlooms(self: *Gpu, items: []const u8, item_off: []const u64, bloom_of_item: []const u32, blooms: []types.LogsBloom) Error!void {
         if (c.phant_gpu_logs_bloom(self.ctx, items.ptr, item_off.ptr, bloom_of_item.ptr, bloom_of_item.len, blooms.len, @ptrCast(blooms.ptr)) != 0)
