@@ -4,8 +4,10 @@
 Workload (BASELINE.json configs[1]): synthetic account proofs, depth 8, 532-byte branch nodes,
 1,000,000 proofs PER GPU (weak scaling: rank r verifies proofs [r*1M, (r+1)*1M) of the same PRNG
 stream).  A "step" is one pass of the hot path over that batch: hash all 8M nodes (batched Keccak
-kernel), walk all proofs, and -- at N > 1 -- one NCCL all-reduce that assembles the global accept
-bitmap on every rank.
+kernel), walk all proofs, and -- at N > 1 -- ONE all-gather of the accept words, issued by the library
+itself (phant_gpu_verify_proofs_sharded, comm.cu) on its comm stream, which leaves the whole accept
+bitmap on every rank.  Multi-GPU goes through the C ABI; torch.distributed only carries the 128-byte
+communicator id, the barriers and the max-over-ranks of the timings.
 
   value        proofs/s, whole job, witnesses already resident in HBM (device-pointer ABI), CUDA events,
                max over ranks
@@ -15,6 +17,9 @@ bitmap on every rank.
   roofline     dominant kernel = batched Keccak; algorithmic bytes = 3,900 B/proof
   cpu_baseline the CPU path on this box's host cores (oracle walk over the reference's compiled
                keccak.c when oracle/_ref is present), bounded sample
+  c3 / c4 / c4_sparse / c5 / keccak_mh_s_532 / keccak_mh_s_112
+               the other BASELINE.json configs in the same line, each with its own device timing, roofline
+               and parity flag (c3: the fixed 10M batch sharded = strong scaling; c5: blocks sharded)
   --impl reference   the CPU arm alone, same metric / config
 """
 import argparse
@@ -25,6 +30,9 @@ import subprocess
 import sys
 import threading
 import time
+
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout at the first communicator: stdout is ONE JSON line
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

@@ -49,7 +49,7 @@ def launches(tag):
     tot = sum(v[1] for v in agg.values())
     ours = sum(v[1] for k, v in agg.items() if "phant::" in k and "synth" not in k)
     with open(os.path.join(OUT, f"launches_{tag}.md"), "w") as f:
-        f.write(f"# ncu launch list, {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 3 --no-cpu`\n"
+        f.write(f"# ncu launch list, {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 3 --no-cpu --skip-extras`\n"
                 "(cold-cache, serialised launches: compare SHARES, not absolutes).  `synth_c2_kernel` is the untimed setup\n"
                 "that generates the witness in HBM; shares below are of the hot path (everything except synth).\n\n")
         f.write("| kernel | launches | total ms | share of hot path |\n|---|---:|---:|---:|\n")
@@ -57,7 +57,7 @@ def launches(tag):
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             share = "setup" if "synth" in k else f"{100 * v[1] / hot:.1f}%"
             f.write(f"| `{k[:90]}` | {v[0]} | {v[1]:.3f} | {share} |\n")
-        f.write(f"\nhand-written phant kernels: {100 * ours / hot:.1f}% of hot-path device time; the rest is CUB (regrouping sort) and torch fills.\n")
+        f.write(f"\nhand-written phant kernels: {100 * ours / hot:.1f}% of hot-path device time; the rest is torch fills / copies (round 2: no library sort on the hot path).\n")
 
 
 def report(tag, which, title):
@@ -98,4 +98,9 @@ if __name__ == "__main__":
         json.dump({"dram_bytes_per_launch": t, "source": f"profiles/keccak_{tag}.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch = 1M proofs)"},
                   open(os.path.join(OUT, "keccak_traffic.json"), "w"))
     report(tag, "walk", "proof-walk kernel (walk_kernel)")
+    import glob
+    for rep in sorted(glob.glob(os.path.join(GO, f"prof_*_{tag}.ncu-rep"))):
+        which = os.path.basename(rep)[len("prof_"):-len(f"_{tag}.ncu-rep")]
+        if which not in ("keccak", "walk"):
+            report(tag, which, f"kernel capture `{which}`")
     print(os.listdir(OUT))
