@@ -31,8 +31,8 @@ import sys
 import threading
 import time
 
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout at the first communicator: stdout is ONE JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]  # at these two levels NCCL printf()s a version banner on stdout; the JSON line is still the LAST line
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
