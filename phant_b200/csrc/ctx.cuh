@@ -46,12 +46,12 @@ struct phant_gpu_ctx {
     DevBuf st_in, st_hash, st_seg, st_tmp, st_sort, st_acc;               // state-root staging
     bool perms_init = false, perms_pending = false;
 
-    std::array<DevBuf*, 42> all_bufs()
+    std::array<DevBuf*, 41> all_bufs()
     {
         return {&d_msgs, &d_off, &d_out, &d_first, &d_keys, &d_roots, &d_digests, &d_bitmap, &d_status, &d_voff, &d_vlen,
                 &d_cls, &d_cls2, &d_idx, &d_order, &d_cub, &d_perms, &d_tmp_a, &d_tmp_b, &d_scan_a, &d_scan_b,
                 &d_b0, &d_b1, &d_b2, &d_b3, &d_b4, &d_b5, &d_b6, &d_b7, &d_b8, &d_b9,
-                &st_in, &st_hash, &st_seg, &st_tmp, &st_sort, &st_acc, &d_summary, &d_index, &d_comm, &d_rej, &d_gtab};
+                &st_in, &st_hash, &st_seg, &st_tmp, &st_sort, &st_acc, &d_summary, &d_index, &d_comm, &d_rej};
     }
 
     // device timing of the dominant kernels: event pairs recorded on `stream`, resolved lazily
@@ -70,8 +70,7 @@ struct phant_gpu_ctx {
     struct Fence { const void* buf; cudaEvent_t ev; };
     std::vector<Fence> fence_events;
     const void* walk_fence_buf = nullptr; // set by the sharded entry point: buffer the next walk launch is about to write
-    DevBuf d_comm, d_rej, d_gtab;  // d_gtab: static odd multiples of the secp256k1 generator (ecrecover.cu)
-    bool gtab_ready = false;
+    DevBuf d_comm, d_rej;
     void* h_comm = nullptr;        // small pinned staging area (subtree roots, counters)
     // peer-memory path (comm.cu): symmetric buffers mapped from every rank of the node
     struct Peer;

@@ -21,22 +21,16 @@ using namespace phant;
 
 namespace {
 
-// the static table of odd multiples of the generator, one entry per thread, once per context
-__global__ void ecrecover_gtable_kernel(uint64_t* __restrict__ tab)
-{
-    if (threadIdx.x < 64) secp::g_table_entry((int)threadIdx.x, tab + 8 * threadIdx.x);
-}
-
 __global__ void __launch_bounds__(128)
 ecrecover_kernel(const uint8_t* __restrict__ hashes32, const uint8_t* __restrict__ sigs65, uint64_t n, uint8_t* __restrict__ pubkeys65,
-                 uint8_t* __restrict__ addresses20, uint8_t* __restrict__ ok, const uint64_t* __restrict__ gtab)
+                 uint8_t* __restrict__ addresses20, uint8_t* __restrict__ ok)
 {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint8_t h[32], sig[65];
         __align__(8) uint8_t pub[64];
         for (int b = 0; b < 32; ++b) h[b] = hashes32[32 * i + b];
         for (int b = 0; b < 65; ++b) sig[b] = sigs65[65 * i + b];
-        const bool good = secp::ecrecover(h, sig, pub, gtab);
+        const bool good = secp::ecrecover(h, sig, pub);
         if (!good)
             for (int b = 0; b < 64; ++b) pub[b] = 0;
         if (pubkeys65) {
@@ -75,17 +69,10 @@ extern "C" int phant_gpu_ecrecover_batch(phant_gpu_ctx* ctx, const uint8_t* hash
         uint8_t* o = (uint8_t*)ctx->d_out.ptr;
         d_pub = pubkeys65 ? o : nullptr; d_addr = addresses20 ? o + 65 * n : nullptr; d_ok = o + 85 * n;
     }
-    if (!ctx->gtab_ready) {
-        if (int rc = ctx->d_gtab.reserve(ctx, 64 * 64)) return rc;
-        ecrecover_gtable_kernel<<<1, 64, 0, s>>>((uint64_t*)ctx->d_gtab.ptr);
-        CU(cudaGetLastError());
-        ctx->gtab_ready = true;
-        ctx->stats.launches++;
-    }
     uint64_t blocks = (n + 127) / 128;
     const uint64_t cap = (uint64_t)keccak_num_sms(ctx->device) * 8;
     if (blocks > cap) blocks = cap;
-    ecrecover_kernel<<<(unsigned)blocks, 128, 0, s>>>(d_h, d_s, n, d_pub, d_addr, d_ok, (const uint64_t*)ctx->d_gtab.ptr);
+    ecrecover_kernel<<<(unsigned)blocks, 128, 0, s>>>(d_h, d_s, n, d_pub, d_addr, d_ok);
     CU(cudaGetLastError());
     ctx->stats.launches++;
     if (!dev) {

@@ -5,29 +5,12 @@
 #define __device__
 #define __forceinline__ inline
 #define __noinline__
-#define __restrict__
 #include "../../phant_b200/csrc/secp256k1.cuh"
 
-// the static generator table, as the context's set-up kernel builds it (one entry per thread there)
-static const uint64_t* gtable()
-{
-    static uint64_t tab[64 * 8];
-    static bool ready = false;
-    if (!ready) {
-        for (int i = 0; i < 64; ++i) phant::secp::g_table_entry(i, tab + 8 * i);
-        ready = true;
-    }
-    return tab;
-}
 extern "C" int host_ecrecover(const uint8_t* hash32, const uint8_t* sig65, uint8_t* pub65)
 {
     pub65[0] = 0x04;
-    return phant::secp::ecrecover(hash32, sig65, pub65 + 1, gtable()) ? 1 : 0;
-}
-extern "C" int host_wnaf(const uint8_t* k32, int w, int8_t* digits /* 264 */)
-{
-    using namespace phant::secp;
-    return w == 8 ? wnaf<8>(from_be(k32), digits) : wnaf<4>(from_be(k32), digits);
+    return phant::secp::ecrecover(hash32, sig65, pub65 + 1) ? 1 : 0;
 }
 extern "C" void host_fp_mul(const uint8_t* a32, const uint8_t* b32, uint8_t* out32)
 {

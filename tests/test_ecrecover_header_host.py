@@ -102,21 +102,3 @@ def test_corner_cases_of_the_double_multiplication(dev, oracle):
     sig = sig65(GX, z, GY & 1)
     assert recover(dev, z.to_bytes(32, "big"), sig) is None and oracle.ecrecover(z.to_bytes(32, "big"), sig) is None
 
-
-def test_wnaf_digits(dev):
-    """width-w non-adjacent form of the device header: digits are zero or odd with |d| < 2^(w-1), any w consecutive positions
-    hold at most one non-zero digit, and sum d_i 2^i is the scalar -- for random and edge scalars, both widths in use"""
-    rng = np.random.default_rng(9)
-    edge = [0, 1, 2, 3, N - 1, N - 2, 2 ** 255, 2 ** 256 - 1, 2 ** 255 - 1, (1 << 256) - (1 << 128), 0x5555555555555555555555555555555555555555555555555555555555555555,
-            0xAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA, (1 << 255) - 1 + (1 << 254)]
-    buf = (C.c_int8 * 264)()
-    for w in (4, 8):
-        for t in range(400):
-            k = edge[t] if t < len(edge) else int.from_bytes(rng.bytes(32), "big")
-            top = dev.host_wnaf(k.to_bytes(32, "big"), w, buf)
-            d = list(buf)
-            assert sum(v << i for i, v in enumerate(d)) == k, (w, hex(k))
-            nz = [i for i, v in enumerate(d) if v]
-            assert all(d[i] % 2 and abs(d[i]) < (1 << (w - 1)) for i in nz)
-            assert all(b - a >= w for a, b in zip(nz, nz[1:]))
-            assert top == (nz[-1] + 1 if nz else 0) and top <= 258
