@@ -90,6 +90,8 @@ struct phant_gpu_ctx {
     int build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off, uint32_t n,
                      const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots,
                      int slots_hint = 0 /* > 0: slot layout with this leaf stride; < 0: decide on the device; 0: general layout */,
-                     uint32_t start_depth = 0 /* key nibbles consumed above every segment's root */);
+                     uint32_t start_depth = 0 /* key nibbles consumed above every segment's root */,
+                     const uint8_t* d_leaf_cache = nullptr /* n x 33: leaf references of an earlier build (resident tries), see trie.cu */,
+                     uint8_t* d_leaf_cache_out = nullptr /* n x 33: the references of this build */);
     int sort_by_segment_and_hash(const uint8_t* d_hashes, const uint32_t* d_seg, uint32_t n, uint32_t* d_perm_out, DevBuf& scratch);
 };

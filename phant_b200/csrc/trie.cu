@@ -251,9 +251,11 @@ struct Vals {
     const uint64_t* off;
 };
 
-__global__ void leaf_size_kernel(Keys k, Vals vals, Tables t, uint32_t n, uint64_t* __restrict__ size)
+// ids (nullable): work item j is key ids[j] (the leaves that still have to be encoded when a leaf-reference cache is in use)
+__global__ void leaf_size_kernel(Keys k, Vals vals, Tables t, uint32_t n, uint64_t* __restrict__ size, const uint32_t* __restrict__ ids)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = ids ? ids[j] : j;
         const uint32_t ls = t.leaf_start[i];
         uint64_t sz = 0;
         if (ls != NONE) {
@@ -263,19 +265,21 @@ __global__ void leaf_size_kernel(Keys k, Vals vals, Tables t, uint32_t n, uint64
             const uint64_t payload = str_size(hpn, hp_first_byte(k, i, ls, nl, true)) + str_size(vl, vl ? vals.bytes[vals.off[i]] : 0);
             sz = hdr_size(payload) + payload;
         }
-        size[i] = sz;
+        size[j] = sz;
     }
 }
 // one warp per leaf: lane 0 writes the headers and the path, all lanes copy the value
 __global__ void __launch_bounds__(256)
 leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __restrict__ aoff, uint8_t* __restrict__ arena,
-                   uint64_t* __restrict__ size_out /*nullable: slot layout, the encoder reports the sizes itself*/)
+                   uint64_t* __restrict__ size_out /*nullable: slot layout, the encoder reports the sizes itself*/,
+                   const uint32_t* __restrict__ ids /*nullable: work item j is key ids[j]*/)
 {
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t i = ids ? ids[j] : j;
         const uint32_t ls = t.leaf_start[i];
-        if (ls == NONE) { if (size_out && lane == 0) size_out[i] = 0; continue; }
-        uint8_t* out = arena + aoff[i];
+        if (ls == NONE) { if (size_out && lane == 0) size_out[j] = 0; continue; }
+        uint8_t* out = arena + aoff[j];
         const uint32_t nl = nlen(k, i);
         const uint32_t hpn = hp_size(nl - ls);
         const uint64_t vl = vals.off[i + 1] - vals.off[i];
@@ -284,7 +288,7 @@ leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __re
         const uint64_t s_hp = str_size(hpn, hp0), s_v = str_size(vl, vl ? v[0] : 0);
         const uint32_t h = hdr_size(s_hp + s_v);
         if (lane == 0) {
-            if (size_out) size_out[i] = h + s_hp + s_v;
+            if (size_out) size_out[j] = h + s_hp + s_v;
             put_hdr(out, s_hp + s_v, 0xc0, 0xf7);
             uint8_t* q = out + h;
             if (s_hp > hpn) q += put_hdr(q, hpn, 0x80, 0xb7);
@@ -295,6 +299,41 @@ leaf_encode_kernel(Keys k, Vals vals, Tables t, uint32_t n, const uint64_t* __re
         uint8_t* dst = out + h + s_hp + (s_v - vl);
         for (uint64_t b = lane; b < vl; b += 32) dst[b] = v[b];
     }
+}
+// Leaf-reference cache (resident tries): row i = [leaf_start + 1 (0 = nothing cached)] + the 32-byte digest of key i's leaf as
+// it was last encoded.  A leaf's encoding depends on (key, the nibble its path starts at, value) only, so a row whose depth
+// byte matches needs neither encode nor hash: its reference is written here and the key is left out of the to-do list.
+__global__ void leaf_cache_probe_kernel(Tables t, uint32_t n, const uint8_t* __restrict__ cache, uint8_t* __restrict__ leaf_digests,
+                                        uint32_t* __restrict__ todo_flag)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t ls = t.leaf_start[i];
+        const uint8_t* row = cache + 33ull * i;
+        const bool hit = ls != NONE && ls < 255 && row[0] == (uint8_t)(ls + 1);
+        todo_flag[i] = hit ? 0 : 1;
+        if (hit) {
+            uint8_t* r = t.ref + 33ull * i;
+            r[0] = 0xa0;
+            for (uint32_t b = 0; b < 32; ++b) { r[1 + b] = row[1 + b]; leaf_digests[32ull * i + b] = row[1 + b]; }
+            t.ref_len[i] = 33;
+        }
+    }
+}
+__global__ void leaf_cache_store_kernel(Tables t, uint32_t n, const uint8_t* __restrict__ leaf_digests, uint8_t* __restrict__ cache_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t ls = t.leaf_start[i];
+        uint8_t* row = cache_out + 33ull * i;
+        const bool hashed = ls != NONE && ls < 255 && t.ref_len[i] == 33; // embedded leaves (< 32 bytes) are never cached
+        row[0] = hashed ? (uint8_t)(ls + 1) : 0;
+        if (hashed)
+            for (uint32_t b = 0; b < 32; ++b) row[1 + b] = leaf_digests[32ull * i + b];
+    }
+}
+__global__ void compact_iota_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i]) out[pos[i]] = i;
 }
 // reference of item j (leaf or encoded unit): raw RLP when < 32 bytes, else 0xa0 || digest
 __global__ void finalize_ref_kernel(uint32_t cnt, const uint32_t* __restrict__ ids /*nullable: identity*/, uint32_t id_base,
@@ -471,7 +510,7 @@ int scan_sizes(phant_gpu_ctx* ctx, uint64_t* sizes, uint64_t* offs, uint64_t cnt
 // ------------------------------------------------------------------------------------------------
 int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off, const uint8_t* d_vals, const uint64_t* d_val_off,
                                 uint32_t n, const uint32_t* d_seg_off, uint32_t n_seg, const uint32_t* d_seg_of_key, uint8_t* d_roots,
-                                int slots_hint, uint32_t start_depth)
+                                int slots_hint, uint32_t start_depth, const uint8_t* d_leaf_cache, uint8_t* d_leaf_cache_out)
 {
     phant_gpu_ctx* ctx = this;
     cudaStream_t s = stream;
@@ -567,30 +606,56 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         stats.launches += 3;
     }
 
-    // ---- leaves: sizes -> offsets -> encode -> hash -> references ----
+    // ---- leaves: sizes -> offsets -> encode -> hash -> references (only the leaves the cache cannot answer) ----
     uint8_t* leaf_digests = nullptr;
     if (n) {
-        RC(d_b4.reserve(ctx, 8ull * (n + 1) * 2));
-        uint64_t* sizes = (uint64_t*)d_b4.ptr;
-        uint64_t* offs = sizes + (n + 1);
-        if (!slots) leaf_size_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(k, vals, t, n, sizes);
-        uint64_t total = (uint64_t)n * leaf_stride;
-        if (slots) offs = fixed_leaf;
-        else {
-            RC(scan_sizes(ctx, sizes, offs, n));
-            CU(cudaMemcpyAsync(&total, offs + n, 8, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-        }
-        RC(d_b5.reserve(ctx, total + 64));
         RC(d_b6.reserve(ctx, 32ull * n));
         leaf_digests = (uint8_t*)d_b6.ptr;
-        leaf_encode_kernel<<<grid1d(device, n, 256, 32), 256, 0, s>>>(k, vals, t, n, offs, (uint8_t*)d_b5.ptr, slots ? sizes : nullptr);
-        stats.launches += slots ? 1 : 2;
-        if (slots) RC(hash_slots((const uint8_t*)d_b5.ptr, offs, sizes, n, leaf_digests));
-        else RC(hash_csr((const uint8_t*)d_b5.ptr, offs, n, total, leaf_digests));
-        finalize_ref_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(n, nullptr, 0, offs, slots ? sizes : nullptr, (const uint8_t*)d_b5.ptr, leaf_digests, 0, t,
-                                                                 nullptr);
-        stats.launches++;
+        uint32_t m = n;                 // leaves to encode
+        const uint32_t* ids = nullptr;  // their key indices (nullptr = all, in order)
+        if (d_leaf_cache) {
+            RC(d_tmp_a.reserve(ctx, 4ull * (n + 2) * 3));
+            uint32_t* flag = (uint32_t*)d_tmp_a.ptr;
+            uint32_t* pos = flag + n + 2;
+            uint32_t* list = pos + n + 2;
+            leaf_cache_probe_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(t, n, d_leaf_cache, leaf_digests, flag);
+            CU(cudaMemsetAsync(flag + n, 0, 4, s));
+            size_t temp = 0;
+            CU(cub::DeviceScan::ExclusiveSum(nullptr, temp, (const uint32_t*)flag, pos, (int64_t)(n + 1), s));
+            RC(d_cub.reserve(ctx, temp));
+            CU(cub::DeviceScan::ExclusiveSum(d_cub.ptr, temp, (const uint32_t*)flag, pos, (int64_t)(n + 1), s));
+            compact_iota_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(flag, pos, n, list);
+            CU(cudaMemcpyAsync(&m, pos + n, 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            ids = list;
+            stats.launches += 3;
+        }
+        if (m) {
+            RC(d_b4.reserve(ctx, 8ull * (m + 1) * 2 + 32ull * m + 64));
+            uint64_t* sizes = (uint64_t*)d_b4.ptr;
+            uint64_t* offs = sizes + (m + 1);
+            uint8_t* dg = ids ? (uint8_t*)(((uintptr_t)(offs + (m + 1)) + 15) & ~(uintptr_t)15) : leaf_digests; // compact digests when indirect
+            if (!slots) leaf_size_kernel<<<grid1d(device, m, 256), 256, 0, s>>>(k, vals, t, m, sizes, ids);
+            uint64_t total = (uint64_t)m * leaf_stride;
+            if (slots) offs = fixed_leaf;
+            else {
+                RC(scan_sizes(ctx, sizes, offs, m));
+                CU(cudaMemcpyAsync(&total, offs + m, 8, cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+            }
+            RC(d_b5.reserve(ctx, total + 64));
+            leaf_encode_kernel<<<grid1d(device, m, 256, 32), 256, 0, s>>>(k, vals, t, m, offs, (uint8_t*)d_b5.ptr, slots ? sizes : nullptr, ids);
+            stats.launches += slots ? 1 : 2;
+            if (slots) RC(hash_slots((const uint8_t*)d_b5.ptr, offs, sizes, m, dg));
+            else RC(hash_csr((const uint8_t*)d_b5.ptr, offs, m, total, dg));
+            finalize_ref_kernel<<<grid1d(device, m, 256), 256, 0, s>>>(m, ids, 0, offs, slots ? sizes : nullptr, (const uint8_t*)d_b5.ptr, dg, 0, t,
+                                                                     ids ? leaf_digests : nullptr);
+            stats.launches++;
+        }
+        if (d_leaf_cache_out) {
+            leaf_cache_store_kernel<<<grid1d(device, n, 256), 256, 0, s>>>(t, n, leaf_digests, d_leaf_cache_out);
+            stats.launches++;
+        }
     }
 
     // ---- units, deepest level first: branch, then the extension above it where there is one ----
@@ -1388,13 +1453,13 @@ struct SRec { uint64_t off; uint32_t len; uint32_t pad; };
 
 struct SparseTrie {
     uint64_t n = 0;
-    DevBuf keys[2], recs[2]; // sorted keys / records, ping-pong across merges
+    DevBuf keys[2], recs[2], cache[2]; // sorted keys / records / leaf-reference cache rows (33 B), ping-pong across merges
     int cur = 0;
     DevBuf arena;
     uint64_t arena_used = 0;
     uint32_t L = 0;
     DevBuf top, present;     // levels 0..L: 32-byte reference + presence byte per node; level d starts at node (16^d - 1) / 15
-    DevBuf sa, sb, sc, sd, se, sf, sg, sh, sroots, ssort; // scratch
+    DevBuf sa, sb, sc, sd, se, sf, sg, sh, si, sroots, ssort; // scratch
     uint8_t root[32];
     uint64_t updates = 0, rebuilds = 0;
 };
@@ -1462,7 +1527,7 @@ __global__ void st_gather_voff_kernel(const uint32_t* __restrict__ raw_voff, con
 }
 __global__ void st_append_kernel(const uint8_t* __restrict__ dv, const uint32_t* __restrict__ dvoff, const uint32_t* __restrict__ dlen,
                                  const uint8_t* __restrict__ kind, const uint32_t* __restrict__ lb, const uint64_t* __restrict__ app_off, uint32_t m, uint64_t arena_base,
-                                 uint8_t* __restrict__ arena, SRec* __restrict__ recs_cur, SRec* __restrict__ drec)
+                                 uint8_t* __restrict__ arena, SRec* __restrict__ recs_cur, SRec* __restrict__ drec, uint8_t* __restrict__ cache_cur)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -1475,7 +1540,7 @@ __global__ void st_append_kernel(const uint8_t* __restrict__ dv, const uint32_t*
         if (lane == 0) {
             const SRec r{dst, len, 0};
             drec[j] = r;
-            if (k == 1) recs_cur[lb[j]] = r;
+            if (k == 1) { recs_cur[lb[j]] = r; cache_cur[33ull * lb[j]] = 0; } // new value: the cached leaf reference is stale
         }
     }
 }
@@ -1486,7 +1551,7 @@ __global__ void st_keep_kernel(const uint32_t* __restrict__ del_flag, uint32_t n
 // merged table: kept table entries and inserts at their final positions
 __global__ void st_merge_table_kernel(const uint8_t* __restrict__ keys, const SRec* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ del_flag,
                                       const uint32_t* __restrict__ K /*excl scan of keep, n*/, const uint32_t* __restrict__ I /*excl scan of ins_at, n+2*/,
-                                      uint8_t* __restrict__ keys_out, SRec* __restrict__ recs_out)
+                                      uint8_t* __restrict__ keys_out, SRec* __restrict__ recs_out, const uint8_t* __restrict__ cache, uint8_t* __restrict__ cache_out)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (del_flag[i]) continue;
@@ -1495,12 +1560,13 @@ __global__ void st_merge_table_kernel(const uint8_t* __restrict__ keys, const SR
         uint4* d = reinterpret_cast<uint4*>(keys_out + 32ull * p);
         d[0] = s[0]; d[1] = s[1];
         recs_out[p] = recs[i];
+        for (uint32_t b = 0; b < 33; ++b) cache_out[33ull * p + b] = cache[33ull * i + b];
     }
 }
 __global__ void st_merge_dirty_kernel(const uint8_t* __restrict__ dk, const SRec* __restrict__ drec, const uint8_t* __restrict__ kind,
                                       const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ins_index, uint32_t m, uint32_t n,
                                       const uint32_t* __restrict__ K /*n+1 entries valid: K[n] = kept total*/, uint8_t* __restrict__ keys_out,
-                                      SRec* __restrict__ recs_out)
+                                      SRec* __restrict__ recs_out, uint8_t* __restrict__ cache_out)
 {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         if (kind[j] != 2) continue;
@@ -1509,6 +1575,7 @@ __global__ void st_merge_dirty_kernel(const uint8_t* __restrict__ dk, const SRec
         uint4* d = reinterpret_cast<uint4*>(keys_out + 32ull * p);
         d[0] = s[0]; d[1] = s[1];
         recs_out[p] = drec[j];
+        cache_out[33ull * p] = 0; // a new key has no cached leaf reference
     }
 }
 // bucket of each dirty key + "first of its bucket" flag
@@ -1551,7 +1618,8 @@ __global__ void st_bucket_range_kernel(const uint8_t* __restrict__ table, uint32
 // gather the keys of the listed buckets into a contiguous forest input (warp per bucket)
 __global__ void st_gather_keys_kernel(const uint8_t* __restrict__ table, const SRec* __restrict__ recs, const uint32_t* __restrict__ lo,
                                       const uint32_t* __restrict__ seg_off, uint32_t nb, uint8_t* __restrict__ gkeys, uint32_t* __restrict__ gkey_off,
-                                      uint32_t* __restrict__ seg_of_key, uint64_t* __restrict__ gval_size, SRec* __restrict__ grec)
+                                      uint32_t* __restrict__ seg_of_key, uint64_t* __restrict__ gval_size, SRec* __restrict__ grec,
+                                      const uint8_t* __restrict__ cache, uint8_t* __restrict__ gcache)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -1566,7 +1634,20 @@ __global__ void st_gather_keys_kernel(const uint8_t* __restrict__ table, const S
             const SRec r = recs[from + t];
             gval_size[base + t] = r.len;
             grec[base + t] = r;
+            for (uint32_t b = 0; b < 33; ++b) gcache[33ull * (base + t) + b] = cache[33ull * (from + t) + b];
         }
+    }
+}
+// the leaf references of this build back into the table's cache rows
+__global__ void st_scatter_cache_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ seg_off, uint32_t nb, const uint8_t* __restrict__ gcache_out,
+                                        uint8_t* __restrict__ cache)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < nb; u += warps) {
+        const uint32_t base = seg_off[u], cnt = seg_off[u + 1] - base, from = lo[u];
+        for (uint32_t t = lane; t < cnt; t += 32)
+            for (uint32_t b = 0; b < 33; ++b) cache[33ull * (from + t) + b] = gcache_out[33ull * (base + t) + b];
     }
 }
 __global__ void st_gather_vals_kernel(const uint8_t* __restrict__ arena, const SRec* __restrict__ grec, const uint64_t* __restrict__ gval_off, uint32_t mk,
@@ -1694,7 +1775,11 @@ int st_rebuild(phant_gpu_trie* t, const uint32_t* d_list, uint32_t nb, bool all)
         SRec* grec = (SRec*)(gvoff + mk + 2);
         uint32_t* gkoff = (uint32_t*)(grec + mk);
         uint32_t* seg_of_key = gkoff + mk + 2;
-        st_gather_keys_kernel<<<grid1d(dev, nb, 256, 32), 256, 0, s>>>(table, recs, lo, seg_off, nb, gkeys, gkoff, seg_of_key, gsize, grec);
+        RC(sp->si.reserve(ctx, 66ull * mk + 64));
+        uint8_t* gcache = (uint8_t*)sp->si.ptr;
+        uint8_t* gcache_out = gcache + 33ull * mk;
+        uint8_t* cache_tab = (uint8_t*)sp->cache[sp->cur].ptr;
+        st_gather_keys_kernel<<<grid1d(dev, nb, 256, 32), 256, 0, s>>>(table, recs, lo, seg_off, nb, gkeys, gkoff, seg_of_key, gsize, grec, cache_tab, gcache);
         const uint32_t last = 32u * mk;
         CU(cudaMemcpyAsync(gkoff + mk, &last, 4, cudaMemcpyHostToDevice, s));
         RC(scan_sizes(ctx, gsize, gvoff, mk));
@@ -1704,7 +1789,9 @@ int st_rebuild(phant_gpu_trie* t, const uint32_t* d_list, uint32_t nb, bool all)
         RC(sp->sd.reserve(ctx, vbytes + 64));
         st_gather_vals_kernel<<<grid1d(dev, mk, 256, 32), 256, 0, s>>>((const uint8_t*)sp->arena.ptr, grec, gvoff, mk, (uint8_t*)sp->sd.ptr);
         ctx->stats.launches += 3;
-        RC(ctx->build_forest(gkeys, gkoff, (const uint8_t*)sp->sd.ptr, gvoff, mk, seg_off, nb, seg_of_key, (uint8_t*)sp->sroots.ptr, -1, L));
+        RC(ctx->build_forest(gkeys, gkoff, (const uint8_t*)sp->sd.ptr, gvoff, mk, seg_off, nb, seg_of_key, (uint8_t*)sp->sroots.ptr, -1, L, gcache, gcache_out));
+        st_scatter_cache_kernel<<<grid1d(dev, nb, 256, 32), 256, 0, s>>>(lo, seg_off, nb, gcache_out, cache_tab);
+        ctx->stats.launches++;
     }
     if (L == 0) { // one bucket: its root is the trie's root
         CU(cudaMemcpyAsync(sp->root, sp->sroots.ptr, 32, cudaMemcpyDeviceToHost, s));
@@ -1849,7 +1936,8 @@ int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, 
         sp->arena = bigger;
     }
     SRec* recs_cur = (SRec*)sp->recs[sp->cur].ptr;
-    st_append_kernel<<<grid1d(dev, m, 256, 32), 256, 0, s>>>(dv, dvoff, dlen, kind, lb, app_off, m, sp->arena_used, (uint8_t*)sp->arena.ptr, recs_cur, drec);
+    st_append_kernel<<<grid1d(dev, m, 256, 32), 256, 0, s>>>(dv, dvoff, dlen, kind, lb, app_off, m, sp->arena_used, (uint8_t*)sp->arena.ptr, recs_cur, drec,
+                                                            (uint8_t*)sp->cache[sp->cur].ptr);
     sp->arena_used += app_bytes;
     ctx->stats.launches++;
     // ---- merge (skipped for pure value updates) ----
@@ -1858,14 +1946,16 @@ int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, 
         const int nxt = 1 - sp->cur;
         RC(sp->keys[nxt].reserve(ctx, 32ull * new_n + 64));
         RC(sp->recs[nxt].reserve(ctx, 16ull * new_n + 64));
+        RC(sp->cache[nxt].reserve(ctx, 33ull * new_n + 64));
         st_keep_kernel<<<grid1d(dev, n + 1, 256), 256, 0, s>>>(del_flag, n, keep);
         RC(st_scan_u32(ctx, keep, Kscan, n + 1));
         RC(st_scan_u32(ctx, ins_at, Iscan, n + 2));
         if (n)
             st_merge_table_kernel<<<grid1d(dev, n, 256), 256, 0, s>>>((const uint8_t*)sp->keys[sp->cur].ptr, recs_cur, n, del_flag, Kscan, Iscan,
-                                                                     (uint8_t*)sp->keys[nxt].ptr, (SRec*)sp->recs[nxt].ptr);
+                                                                     (uint8_t*)sp->keys[nxt].ptr, (SRec*)sp->recs[nxt].ptr,
+                                                                     (const uint8_t*)sp->cache[sp->cur].ptr, (uint8_t*)sp->cache[nxt].ptr);
         st_merge_dirty_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(dk, drec, kind, lb, ins_index, m, n, Kscan, (uint8_t*)sp->keys[nxt].ptr,
-                                                                 (SRec*)sp->recs[nxt].ptr);
+                                                                 (SRec*)sp->recs[nxt].ptr, (uint8_t*)sp->cache[nxt].ptr);
         ctx->stats.launches += 5;
         sp->cur = nxt;
         sp->n = new_n;
@@ -2118,7 +2208,7 @@ extern "C" void phant_gpu_trie_close(phant_gpu_trie* t)
     t->work.release();
     if (t->sp) {
         SparseTrie* sp = t->sp;
-        for (DevBuf* b : {&sp->keys[0], &sp->keys[1], &sp->recs[0], &sp->recs[1], &sp->arena, &sp->top, &sp->present, &sp->sa, &sp->sb, &sp->sc, &sp->sd,
+        for (DevBuf* b : {&sp->keys[0], &sp->keys[1], &sp->recs[0], &sp->recs[1], &sp->cache[0], &sp->cache[1], &sp->si, &sp->arena, &sp->top, &sp->present, &sp->sa, &sp->sb, &sp->sc, &sp->sd,
                           &sp->se, &sp->sf, &sp->sg, &sp->sh, &sp->sroots, &sp->ssort}) b->release();
         delete sp;
     }

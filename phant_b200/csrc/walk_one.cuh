@@ -149,7 +149,6 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
     } else if (first == last) return eq32_const(EMPTY_ROOT, expect) ? ST_ABSENT : ST_REJECT;
 
     uint32_t pos = 0; // nibbles of the key consumed
-    uint64_t prev_end = 0;
     uint64_t i = first;
     const uint8_t* cur = nullptr;
     uint32_t cur_len = 0;
@@ -167,10 +166,8 @@ __device__ int walk_one(const uint8_t* __restrict__ nodes, const uint64_t* __res
                 if (i == last) return ST_REJECT; // R3: a hash reference needs a node
                 ni = node_index ? node_index[i] : i; // deduplicated witness: the chain holds node indices
             }
-            // contiguous chains (no index list): node i starts where node i - 1 ended -- one offset load per node, not two
-            const uint64_t o = (!BAG && !node_index && i > first) ? prev_end : node_off[ni];
-            prev_end = node_off[ni + 1];
-            const uint64_t l = prev_end - o;
+            const uint64_t o = node_off[ni];
+            const uint64_t l = node_off[ni + 1] - o;
             if (l > 0xffffffffull) return ST_REJECT;
             cur = nodes + o;
             cur_len = (uint32_t)l;
