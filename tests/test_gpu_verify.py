@@ -403,3 +403,34 @@ def test_full_size_status_and_values_vs_oracle(ctx, oracle, which, n, chunk):
         assert ok.sum() > 0.98 * chunk
         assert (got[2][ok] == want[2][ok]).all() and (got[3][ok] == want[3][ok]).all()
         assert (want[1] == np.where((np.arange(chunk) + lo) % 97 == 0, 0, 1)).all()
+
+
+def test_device_built_block_witnesses_vs_oracle(ctx, oracle):
+    """the C5 workload bench.py measures is BUILT on the device (phant_b200/synth_blocks.py: torch lays the bytes out, the
+    library's Keccak hashes every level): what the GPU verifier says about it must be what the oracle says about the same
+    bytes -- statuses, accept bits, value slices, per-block reject counts -- and only block 37 may be refused"""
+    import torch
+    from phant_b200 import gpu, synth_blocks
+    first, nb, txs = 30, 12, 40
+    w = synth_blocks.synth_blocks(ctx, "cuda", first, nb, txs=txs)
+    n = w["n_proofs"]
+    h = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in w.items()}
+    want = oracle.verify_proofs(h["nodes"], h["node_off"].astype(np.uint64), h["proof_first"].astype(np.uint64), h["keys32"], h["roots32"], threads=8,
+                                node_index=h["node_index"].astype(np.uint64))
+    d_status = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+    d_voff = torch.zeros(n, dtype=torch.int64, device="cuda")
+    d_vlen = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros(first + nb, dtype=torch.int32, device="cuda")
+    ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
+    ctx.verify_proofs(n, w["nodes"], w["node_off"], w["proof_first"], w["keys32"], w["roots32"], n, d_bitmap, d_status, d_voff, d_vlen,
+                      n_nodes=w["n_nodes"], nodes_bytes=w["n_bytes"], node_index=w["node_index"])
+    ctx.block_reject_counts(d_status, w["block_of_proof"], n, first + nb, d_counts)
+    ctx.synchronize()
+    ctx.set_flags(0)
+    status = d_status.cpu().numpy()
+    assert (status == want[1]).all() and (d_bitmap.cpu().numpy().view(np.uint64) == want[0]).all()
+    ok = status == 1
+    assert (d_voff.cpu().numpy().view(np.uint64)[ok] == want[2][ok]).all() and (d_vlen.cpu().numpy().view(np.uint32)[ok] == want[3][ok]).all()
+    counts = d_counts.cpu().numpy()
+    assert counts[37] == 1 and counts.sum() == 1 and (status == 0).sum() == 1
