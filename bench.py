@@ -491,6 +491,15 @@ def run_gpu(args, rank, world, local_rank):
             idt.copy_(torch.frombuffer(bytearray(gpu.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         ctx.comm_init(idt.cpu().numpy().tobytes(), rank, world)
+    transport = "none (1 GPU)"
+    if world > 1:
+        transport = "nccl"
+        if os.environ.get("PHANT_BENCH_TRANSPORT", "peer") == "peer":
+            try:  # collective: every rank takes the same branch (the library agrees on the outcome with one all-reduce)
+                ctx.comm_enable_peer(world * PROOFS_PER_GPU)
+                transport = "peer"
+            except gpu.PhantGpuError:
+                transport = "nccl (peer mapping unavailable)"
     n = PROOFS_PER_GPU
     n_global = world * n
     first_index, hi = gpu.shard_range(n_global, rank, world)  # contiguous, 64-aligned proof ranges (weak scaling)
@@ -633,8 +642,12 @@ def run_gpu(args, rank, world, local_rank):
             "dtype": "u64", "data": "synthetic", "config": config(world),
             "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1], "max_over_ranks": step_max,
                         "note": "per-step CUDA events on rank 0's launching stream; ms_per_step = whole timed region (incl. the last gather) / K, max over ranks"},
-            "collective": ("one ncclAllGather of the accept words per step, issued by libphantgpu.so (phant_gpu_verify_proofs_sharded) on its own "
-                           "comm stream behind an event; two bitmap buffers alternate") if world > 1 else "none (1 GPU)",
+            "collective": {"peer": "no collective launch: the walk kernel's epilogue stores its accept words into every rank's bitmap over NVLink peer "
+                                   "mappings and publishes the step; the library's comm stream waits for the peers' words and copies the bitmap out "
+                                   "(phant_gpu_comm_enable_peer + phant_gpu_verify_proofs_sharded); two buffers alternate"}.get(
+                transport, "one ncclAllGather of the accept words per step, issued by libphantgpu.so (phant_gpu_verify_proofs_sharded) on its own "
+                           "comm stream behind an event; two bitmap buffers alternate" if world > 1 else "none (1 GPU)"),
+            "transport": transport, "peer_status": ctx.comm_peer_status() if world > 1 else None,
             "keccak_mh_s": world * n_nodes / (keccak_ms * 1e-3) / 1e6, "keccak_gperm_s": world * perm_s / 1e9,
             "kernel_ms": {"keccak": keccak_ms, "walk": walk_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

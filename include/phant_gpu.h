@@ -228,6 +228,15 @@ int phant_gpu_comm_init(phant_gpu_ctx* ctx, const uint8_t id[PHANT_GPU_COMM_ID_B
 int phant_gpu_comm_init_local(phant_gpu_ctx** ctxs, int n); /* one process: n contexts on n devices, rank i = ctxs[i]; afterwards
                                                                drive each context from its own host thread */
 int phant_gpu_comm_info(const phant_gpu_ctx* ctx, int* rank, int* world, int* nccl_version);
+/* Optional PEER TRANSPORT for the gathered accept bitmap (same node, NVLink): a collective call that maps one small symmetric
+ * region of every rank into every other rank (cudaIpc between processes, peer access inside one process).  Afterwards
+ * device-pointer calls of phant_gpu_verify_proofs_sharded with equal, 64-aligned shards of at most max_n_global proofs need
+ * no collective launch: the walk kernel's epilogue stores each ballot word straight into every rank's gathered bitmap and
+ * publishes the step, and the comm stream only waits for the peers' words and copies the bitmap out.  Everything else keeps
+ * using NCCL.  PHANT_GPU_E_COMM when a mapping is not possible on some rank: nothing changes, NCCL stays in use.  A rank
+ * that stops answering makes the waiting kernels give up after 4 s; phant_gpu_comm_peer_status reports it. */
+int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_global);
+int phant_gpu_comm_peer_status(phant_gpu_ctx* ctx, int* enabled, uint64_t* steps, int* timed_out);
 int phant_gpu_comm_fence(phant_gpu_ctx* ctx);   /* the context's stream waits (on the device) for every collective issued so far */
 int phant_gpu_comm_destroy(phant_gpu_ctx* ctx); /* also done by phant_gpu_destroy */
 /* Rank r of `world` owns proofs [lo, hi): contiguous, every boundary but the last a multiple of 64 so that bitmap words

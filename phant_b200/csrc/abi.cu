@@ -375,7 +375,8 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
         if (accept_bitmap) CU(cudaMemsetAsync(accept_bitmap, 0, bm_bytes, ctx->stream));
         ctx->time_begin(1);
         CU(launch_walk(ctx->stream, ctx->device, np, in->nodes, in->node_off, in->node_index, in->proof_first, in->keys32, in->roots32, in->n_roots,
-                       (const uint8_t*)ctx->d_digests.ptr, (const uint32_t*)ctx->d_summary.ptr, accept_bitmap, status, val_off, val_len));
+                       (const uint8_t*)ctx->d_digests.ptr, (const uint32_t*)ctx->d_summary.ptr, accept_bitmap, status, val_off, val_len,
+                       (const PeerOut*)ctx->walk_peer /* sharded call over the peer transport: fused gather (comm.cu) */));
         ctx->time_end();
         ctx->stats.launches++;
         return PHANT_GPU_OK; // asynchronous on the context's stream: phant_gpu_synchronize() to wait

@@ -18,6 +18,8 @@
 #include "ctx.cuh"
 
 #include <dlfcn.h>
+#include <unistd.h>
+#include <new>
 #include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -131,6 +133,41 @@ __global__ void reject_count_kernel(const uint8_t* __restrict__ status, const ui
 
 } // namespace
 
+// ------------------------------------------------------------------------------------------------
+// peer transport: one symmetric region per rank, mapped into every rank of the node
+// ------------------------------------------------------------------------------------------------
+// region layout: [ready[2][16] u64][done[2][16] u64][err u32, tickets ...] (1 KB header) then 2 gathered-bitmap buffers.
+// ready[b][src] = last step whose words rank `src` has stored into MY buffer b; done[b][src] = last step of buffer b that
+// rank `src` has copied out of ITS buffer b (so I may overwrite it).  Steps count from 1; step s uses buffer s & 1.
+struct phant_gpu_ctx::Peer {
+    int world = 0, rank = 0;
+    uint64_t cap_words = 0;            // per buffer
+    uint8_t* region[PEER_MAX_WORLD] = {}; // every rank's region as mapped here (region[rank] = my own allocation)
+    bool ipc_opened[PEER_MAX_WORLD] = {};
+    uint64_t step = 0;
+    static constexpr size_t HDR = 1024;
+    unsigned long long* ready(int r, int b, int src) const { return (unsigned long long*)region[r] + (b * PEER_MAX_WORLD + src); }
+    unsigned long long* done(int r, int b, int src) const { return (unsigned long long*)region[r] + (2 * PEER_MAX_WORLD + b * PEER_MAX_WORLD + src); }
+    uint32_t* err(int r) const { return (uint32_t*)(region[r] + 8 * 4 * PEER_MAX_WORLD); }
+    uint32_t* ticket(int which) const { return err(rank) + 4 + which; } // my own region only
+    uint64_t* bitmap(int r, int b) const { return (uint64_t*)(region[r] + HDR) + (uint64_t)b * cap_words; }
+};
+
+namespace {
+struct PeerRec { cudaIpcMemHandle_t h; uint64_t pid; uint64_t ptr; int32_t dev; int32_t pad; };
+
+void peer_release(phant_gpu_ctx* ctx)
+{
+    phant_gpu_ctx::Peer* p = ctx->peer;
+    if (!p) return;
+    for (int r = 0; r < p->world; ++r)
+        if (r != p->rank && p->ipc_opened[r]) cudaIpcCloseMemHandle(p->region[r]);
+    if (p->region[p->rank]) cudaFree(p->region[p->rank]);
+    delete p;
+    ctx->peer = nullptr;
+}
+} // namespace
+
 // the walk that is about to write `walk_fence_buf` waits (on the device) for the collective still using that buffer
 int phant_gpu_ctx::wait_walk_fence()
 {
@@ -212,6 +249,23 @@ extern "C" int phant_gpu_comm_init_local(phant_gpu_ctx** ctxs, int n)
     return PHANT_GPU_OK;
 }
 
+extern "C" int phant_gpu_comm_peer_status(phant_gpu_ctx* ctx, int* enabled, uint64_t* steps, int* timed_out)
+{
+    if (!ctx) return PHANT_GPU_E_INVALID;
+    if (enabled) *enabled = ctx->peer ? 1 : 0;
+    if (steps) *steps = ctx->peer ? ctx->peer->step : 0;
+    if (timed_out) {
+        *timed_out = 0;
+        if (ctx->peer) {
+            CU(cudaSetDevice(ctx->device));
+            uint32_t e = 0;
+            CU(cudaMemcpy(&e, ctx->peer->err(ctx->peer->rank), 4, cudaMemcpyDeviceToHost));
+            *timed_out = (int)e;
+        }
+    }
+    return PHANT_GPU_OK;
+}
+
 extern "C" int phant_gpu_comm_info(const phant_gpu_ctx* ctx, int* rank, int* world, int* nccl_version)
 {
     if (!ctx) return PHANT_GPU_E_INVALID;
@@ -229,7 +283,17 @@ extern "C" int phant_gpu_comm_destroy(phant_gpu_ctx* ctx)
 {
     if (!ctx) return PHANT_GPU_E_INVALID;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    if (ctx->peer) {
+        // nobody may unmap or free a region a peer's kernels could still be storing into: one collective as the barrier
+        NcclApi* api = nccl_api();
+        if (api && ctx->comm && ctx->d_comm.ptr) {
+            api->AllReduce(ctx->d_comm.ptr, ctx->d_comm.ptr, 1, ncclInt32, ncclMin, (ncclComm_t)ctx->comm, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
+        peer_release(ctx);
+    }
     if (ctx->comm) {
         NcclApi* api = nccl_api();
         if (api) api->CommDestroy((ncclComm_t)ctx->comm);
@@ -255,6 +319,77 @@ extern "C" int phant_gpu_comm_fence(phant_gpu_ctx* ctx)
     return PHANT_GPU_OK;
 }
 
+extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_global)
+{
+    if (!ctx || max_n_global == 0) return PHANT_GPU_E_INVALID;
+    if (ctx->peer) return PHANT_GPU_OK;
+    const int world = ctx->comm_world, rank = ctx->comm_rank;
+    NcclApi* api = nccl_api();
+    if (world < 2 || world > PEER_MAX_WORLD || !api || !ctx->comm) { snprintf(ctx->last_error, sizeof ctx->last_error, "peer transport needs a communicator of 2..16 ranks"); return PHANT_GPU_E_COMM; }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    auto* p = new (std::nothrow) phant_gpu_ctx::Peer();
+    if (!p) return PHANT_GPU_E_OOM;
+    p->world = world; p->rank = rank;
+    p->cap_words = phant_gpu_sharded_bitmap_words(max_n_global, world);
+    const size_t bytes = phant_gpu_ctx::Peer::HDR + 2 * 8 * p->cap_words + 64;
+    uint8_t* mine = nullptr;
+    int ok_local = 1;
+    if (cudaMalloc((void**)&mine, bytes) != cudaSuccess) { cudaGetLastError(); ok_local = 0; }
+    PeerRec* h = (PeerRec*)ctx->h_comm;
+    static_assert(sizeof(PeerRec) == 88, "record layout");
+    if ((size_t)(world + 1) * sizeof(PeerRec) > 16384) { if (mine) cudaFree(mine); delete p; return PHANT_GPU_E_INVALID; }
+    memset(h, 0, sizeof(PeerRec));
+    if (ok_local) {
+        CU(cudaMemsetAsync(mine, 0, bytes, s));
+        if (cudaIpcGetMemHandle(&h->h, mine) != cudaSuccess) { cudaGetLastError(); ok_local = 0; }
+        h->pid = (uint64_t)getpid(); h->ptr = (uint64_t)(uintptr_t)mine; h->dev = ctx->device;
+    }
+    h->pad = ok_local;
+    if (int rc = ctx->d_comm.reserve(ctx, sizeof(PeerRec) * (world + 1))) { if (mine) cudaFree(mine); delete p; return rc; }
+    uint8_t* d = (uint8_t*)ctx->d_comm.ptr;
+    CU(cudaMemcpyAsync(d + sizeof(PeerRec) * rank, h, sizeof(PeerRec), cudaMemcpyHostToDevice, s));
+    NC(api->AllGather(d + sizeof(PeerRec) * rank, d, sizeof(PeerRec), ncclUint8, (ncclComm_t)ctx->comm, s));
+    PeerRec* all = h + 1;
+    CU(cudaMemcpyAsync(all, d, sizeof(PeerRec) * world, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // every rank takes the same decision from the same records; mapping failures are exchanged in a second round
+    int ok = 1;
+    for (int r = 0; r < world; ++r) ok &= all[r].pad;
+    p->region[rank] = mine;
+    for (int r = 0; ok && r < world; ++r) {
+        if (r == rank) continue;
+        if (all[r].pid == (uint64_t)getpid()) { // one process, several contexts: plain peer access
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctx->device, all[r].dev);
+            if (!can) { ok = 0; break; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[r].dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+            cudaGetLastError();
+            p->region[r] = (uint8_t*)(uintptr_t)all[r].ptr;
+        } else {
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            p->region[r] = (uint8_t*)q;
+            p->ipc_opened[r] = true;
+        }
+    }
+    // agree: one all-reduce (min) of the local verdicts, which is also the barrier "every region is zeroed and mapped"
+    int32_t* flag = (int32_t*)h;
+    *flag = ok;
+    CU(cudaMemcpyAsync(d, flag, 4, cudaMemcpyHostToDevice, s));
+    NC(api->AllReduce(d, d, 1, ncclInt32, ncclMin, (ncclComm_t)ctx->comm, s));
+    CU(cudaMemcpyAsync(flag, d, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    ctx->peer = p;
+    if (!*flag) {
+        peer_release(ctx);
+        snprintf(ctx->last_error, sizeof ctx->last_error, "peer mapping (cudaIpc / peer access) not available on every rank");
+        return PHANT_GPU_E_COMM;
+    }
+    return PHANT_GPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // V, sharded
 // ------------------------------------------------------------------------------------------------
@@ -274,12 +409,49 @@ extern "C" int phant_gpu_verify_proofs_sharded(phant_gpu_ctx* ctx, const phant_g
     if (ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS) {
         // asynchronous: Keccak + walk on the context's stream, the gather on the comm stream behind an event
         uint64_t* mine = global_bitmap + (uint64_t)rank * per_words;
+        const uint64_t my_words = (hi - lo + 63) / 64;
+        phant_gpu_ctx::Peer* pr = ctx->peer;
+        // (the choice must be the same on every rank: it depends on n_global and world only -- equal, 64-aligned shards)
+        if (world > 1 && pr && n_global && n_global % (64ull * world) == 0 && per_words * world <= pr->cap_words) {
+            // ---- peer transport: the walk's epilogue stores into every rank's buffer and publishes the step; the comm stream
+            // only waits for the other ranks' words, copies the gathered bitmap out and releases the buffer ----
+            NvtxRange nvtx("phant:gather(peer)");
+            const unsigned long long step = ++pr->step;
+            const int b = (int)(step & 1);
+            PeerOut po{};
+            for (int r = 0; r < world; ++r) {
+                po.dst[r] = (uint32_t*)(pr->bitmap(r, b) + (uint64_t)rank * per_words);
+                po.ready[r] = pr->ready(r, b, rank);
+            }
+            po.done = pr->done(rank, b, 0);
+            po.wait_done = step > 2 ? step - 2 : 0;
+            po.step = step;
+            po.ticket = pr->ticket(0);
+            po.err = pr->err(rank);
+            po.world = (uint32_t)world;
+            ctx->walk_peer = &po;
+            const int rc = phant_gpu_verify_proofs(ctx, local, nullptr, status, val_off, val_len);
+            ctx->walk_peer = nullptr;
+            if (rc) return rc;
+            cudaEvent_t done_ev = fence_for(ctx, global_bitmap);
+            if (!done_ev) return PHANT_GPU_E_CUDA;
+            CU(cudaEventRecord(ctx->ev_compute, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
+            PeerOut sig{};
+            for (int r = 0; r < world; ++r) sig.ready[r] = pr->done(r, b, rank);
+            sig.ticket = pr->ticket(1);
+            sig.err = pr->err(rank);
+            CU(launch_peer_collect(ctx->comm_stream, pr->ready(rank, b, 0), (uint32_t)world, step, pr->bitmap(rank, b), global_bitmap,
+                                   8 * per_words * world, sig));
+            CU(cudaEventRecord(done_ev, ctx->comm_stream));
+            ctx->stats.launches++;
+            return PHANT_GPU_OK;
+        }
         if (world > 1) ctx->walk_fence_buf = global_bitmap; // the walk waits for the collective that still uses this buffer
         if (local->n_proofs) {
             if (int rc = phant_gpu_verify_proofs(ctx, local, mine, status, val_off, val_len)) return rc;
         } else if (int rc = ctx->wait_walk_fence()) return rc;
         if (world == 1) return PHANT_GPU_OK;
-        const uint64_t my_words = (hi - lo + 63) / 64;
         if (my_words < per_words) CU(cudaMemsetAsync(mine + my_words, 0, 8 * (per_words - my_words), ctx->stream)); // short / empty last shard
         NvtxRange nvtx("phant:gather");
         cudaEvent_t done = fence_for(ctx, global_bitmap);

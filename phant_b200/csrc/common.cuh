@@ -19,11 +19,29 @@ cudaError_t launch_keccak_classify(cudaStream_t s, int device, const uint64_t* o
                                    unsigned long long* perms);
 cudaError_t launch_keccak_regroup(cudaStream_t s, int device, const uint64_t* off, uint64_t n, const uint32_t* start, uint32_t* order);
 
+// Peer-memory epilogue of the proof walk (comm.cu "peer transport"): every warp stores its ballot word straight into the
+// gathered bitmap of EVERY rank of the node through NVLink peer mappings (lane r < world stores to rank r: one predicated
+// store instruction), and the last CTA to finish publishes "step s of rank `me` has landed" in every rank's flag array.
+constexpr int PEER_MAX_WORLD = 16;
+struct PeerOut {
+    uint32_t* dst[PEER_MAX_WORLD];         // rank r's bitmap of this step's buffer, at THIS rank's slice (32-bit words)
+    unsigned long long* ready[PEER_MAX_WORLD]; // in rank r's region: ready[buffer][me]
+    const unsigned long long* done;        // in MY region: done[buffer][0..world): rank r has copied step (value) out of this buffer
+    unsigned long long wait_done;          // wait until done[r] >= this for every r before touching remote memory (0 = no wait)
+    unsigned long long step;               // value to publish
+    uint32_t* ticket;                      // CTA counter (device memory of this rank)
+    uint32_t* err;                         // set to 1 when a wait times out
+    uint32_t world;
+};
+
 // walk_kernel.cu
 cudaError_t launch_walk(cudaStream_t s, int device, uint64_t n_proofs, const uint8_t* nodes, const uint64_t* node_off,
                         const uint64_t* node_index /*nullable*/, const uint64_t* proof_first, const uint8_t* keys32, const uint8_t* roots32, uint64_t n_roots,
                         const uint8_t* digests, const uint32_t* summary /*nullable*/, uint64_t* bitmap, uint8_t* status,
-                        uint64_t* val_off, uint32_t* val_len);
+                        uint64_t* val_off, uint32_t* val_len, const PeerOut* peer = nullptr /*nullable: fused gather over peer memory*/);
+
+cudaError_t launch_peer_collect(cudaStream_t s, const unsigned long long* ready, uint32_t world, unsigned long long step, const void* src, void* dst,
+                                uint64_t bytes, const PeerOut& sig);
 
 cudaError_t launch_bag_build(cudaStream_t s, int device, const uint8_t* digests, uint64_t n_nodes, uint32_t* table, uint32_t capacity);
 cudaError_t launch_walk_bag(cudaStream_t s, int device, uint64_t n_keys, const uint8_t* nodes, const uint64_t* node_off, const uint8_t* keys32,

@@ -75,6 +75,7 @@ struct phant_gpu_ctx {
     // peer-memory path (comm.cu): symmetric buffers mapped from every rank of the node
     struct Peer;
     Peer* peer = nullptr;
+    const void* walk_peer = nullptr; // (const phant::PeerOut*) set by the sharded entry point around one verify call
     int wait_walk_fence();
 
     void time_begin(int which);

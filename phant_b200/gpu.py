@@ -58,7 +58,7 @@ EXPORTS = [
     "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_ecrecover_batch", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
-    "phant_gpu_comm_get_unique_id", "phant_gpu_comm_init", "phant_gpu_comm_init_local", "phant_gpu_comm_info", "phant_gpu_comm_fence",
+    "phant_gpu_comm_get_unique_id", "phant_gpu_comm_init", "phant_gpu_comm_init_local", "phant_gpu_comm_info", "phant_gpu_comm_enable_peer", "phant_gpu_comm_peer_status", "phant_gpu_comm_fence",
     "phant_gpu_comm_destroy", "phant_gpu_shard_range", "phant_gpu_sharded_bitmap_words", "phant_gpu_verify_proofs_sharded",
     "phant_gpu_block_reject_counts", "phant_gpu_nibble_owner", "phant_gpu_state_root_sharded",
 ]
@@ -109,6 +109,8 @@ def _lib():
     L.phant_gpu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.phant_gpu_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
     L.phant_gpu_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.phant_gpu_comm_enable_peer.argtypes = [vp, C.c_uint64]
+    L.phant_gpu_comm_peer_status.argtypes = [vp, C.POINTER(C.c_int), u64p, C.POINTER(C.c_int)]
     L.phant_gpu_comm_fence.argtypes = [vp]
     L.phant_gpu_comm_destroy.argtypes = [vp]
     L.phant_gpu_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
@@ -251,6 +253,16 @@ class Context:
         r, w, v = C.c_int(), C.c_int(), C.c_int()
         self._chk(_lib().phant_gpu_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)), "comm_info")
         return r.value, w.value, v.value
+
+    def comm_enable_peer(self, max_n_global):
+        """collective; afterwards equal-shard device-pointer calls of verify_proofs_sharded gather through peer memory
+        (the walk's epilogue) instead of a NCCL launch.  Raises PhantGpuError(-5) when a mapping is impossible: NCCL stays."""
+        self._chk(_lib().phant_gpu_comm_enable_peer(self._h, max_n_global), "comm_enable_peer")
+
+    def comm_peer_status(self):
+        e, st, to = C.c_int(), C.c_uint64(), C.c_int()
+        self._chk(_lib().phant_gpu_comm_peer_status(self._h, C.byref(e), C.byref(st), C.byref(to)), "comm_peer_status")
+        return {"enabled": bool(e.value), "steps": int(st.value), "timed_out": bool(to.value)}
 
     def comm_fence(self):
         self._chk(_lib().phant_gpu_comm_fence(self._h), "comm_fence")

@@ -76,7 +76,7 @@ def test_world_size_two_through_the_abi_from_cpp():
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
 
 
-def _worker(rank, world, n, tmp):
+def _worker(rank, world, n, tmp, peer=False):
     sys.path.insert(0, HERE)
     sys.path.insert(0, ROOT)
     import time
@@ -94,6 +94,9 @@ def _worker(rank, world, n, tmp):
     ctx = gpu.Context(rank, gpu.FLAG_DEVICE_PTRS)
     ctx.comm_init(open(idf, "rb").read(), rank, world)
     assert ctx.comm_info()[:2] == (rank, world)
+    if peer:
+        ctx.comm_enable_peer(n)   # cudaIpc mappings between the two processes; raises if the box cannot do it
+        assert ctx.comm_peer_status()["enabled"]
     o = oracle_lib.get()
     lo, hi = gpu.shard_range(n, rank, world)
     w = o.synth_c2(hi - lo, depth=8, first=lo, threads=2)
@@ -104,11 +107,14 @@ def _worker(rank, world, n, tmp):
     words = gpu.sharded_bitmap_words(n, world)
     gb = [torch.zeros(words, dtype=torch.int64, device="cuda") for _ in range(2)]
     d_status = torch.zeros(hi - lo, dtype=torch.uint8, device="cuda")
-    for k in range(5):  # alternate the two buffers; steps overlap on the comm stream
+    for k in range(7 if peer else 5):  # alternate the two buffers; steps overlap on the comm stream
         ctx.verify_proofs_sharded(hi - lo, n, d_nodes, d[1], d[2], d[3], d[4], hi - lo, gb[k & 1], d_status)
     ctx.comm_fence()
     ctx.synchronize()
     assert (d_status.cpu().numpy() == want_local[1]).all()
+    if peer:
+        st = ctx.comm_peer_status()
+        assert st["steps"] == 7 and not st["timed_out"], st
     np.save(os.path.join(tmp, f"bitmap_{rank}.npy"), torch.stack(gb).cpu().numpy())
     # host-pointer form
     ctx.set_flags(0)
@@ -126,10 +132,24 @@ def test_two_processes_gather_the_accept_bitmap(tmp_path, oracle):
     stream, then the host-pointer form; every rank must hold the bitmap a single process computes over the whole batch"""
     if _n_gpus() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    n, world = 100_000, 2
+    _check_two_process_gather(tmp_path, oracle, n, world, peer=False)
+
+
+@pytest.mark.gpu
+def test_two_processes_gather_through_peer_memory(tmp_path, oracle):
+    """the same, with the peer transport: the walk kernel's epilogue stores the ballot words into the other process's bitmap
+    through a cudaIpc mapping and publishes the step; no collective launch.  n is chosen so that both shards are equal and
+    64-aligned (the condition for the peer path); the host-pointer form still goes through NCCL."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _check_two_process_gather(tmp_path, oracle, 128 * 1024, 2, peer=True)
+
+
+def _check_two_process_gather(tmp_path, oracle, n, world, peer):
     import torch.multiprocessing as mp
     from phant_b200 import gpu
-    n, world = 100_000, 2
-    mp.spawn(_worker, args=(world, n, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, n, str(tmp_path), peer), nprocs=world, join=True)
     o = oracle.synth_c2(n, depth=8, threads=4)
     want = np.unpackbits(oracle.verify_proofs(*o, threads=4)[0].view(np.uint8), bitorder="little")[:n]
     per = gpu.sharded_bitmap_words(n, world) // world * 64
@@ -140,3 +160,55 @@ def test_two_processes_gather_the_accept_bitmap(tmp_path, oracle):
                 bits = np.unpackbits(row.view(np.uint8), bitorder="little")
                 got = np.concatenate([bits[q * per: q * per + (gpu.shard_range(n, q, world)[1] - gpu.shard_range(n, q, world)[0])] for q in range(world)])
                 assert (got == want).all(), (r, name)
+
+
+@pytest.mark.gpu
+def test_one_process_two_contexts_peer_transport(oracle):
+    """one process, one context + one host thread per GPU (phant_gpu_comm_init_local): the peer transport inside a process is
+    plain peer access (no cudaIpc); five overlapping device-pointer steps per thread, both threads must end with the whole
+    accept bitmap"""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import threading
+    import torch
+    from phant_b200 import gpu
+    n, world = 64 * 1024, 2
+    ctxs = [gpu.Context(r, gpu.FLAG_DEVICE_PTRS) for r in range(world)]
+    gpu.comm_init_local(ctxs)
+    o = oracle.synth_c2(n, depth=8, threads=4)
+    want = oracle.verify_proofs(*o, threads=4)[0]
+    out, errs = [None] * world, []
+
+    def run(r):
+        try:
+            torch.cuda.set_device(r)
+            ctx = ctxs[r]
+            ctx.comm_enable_peer(n)
+            lo, hi = gpu.shard_range(n, r, world)
+            w = oracle.synth_c2(hi - lo, depth=8, first=lo, threads=2)
+            d = [torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(f"cuda:{r}") for a in w]
+            d_nodes = torch.zeros(d[0].numel() + 64, dtype=torch.uint8, device=f"cuda:{r}")
+            d_nodes[:d[0].numel()] = d[0]
+            gb = [torch.zeros(gpu.sharded_bitmap_words(n, world), dtype=torch.int64, device=f"cuda:{r}") for _ in range(2)]
+            d_status = torch.zeros(hi - lo, dtype=torch.uint8, device=f"cuda:{r}")
+            torch.cuda.synchronize(r)
+            for k in range(5):
+                ctx.verify_proofs_sharded(hi - lo, n, d_nodes, d[1], d[2], d[3], d[4], hi - lo, gb[k & 1], d_status)
+            ctx.comm_fence()
+            ctx.synchronize()
+            st = ctx.comm_peer_status()
+            assert st["enabled"] and st["steps"] == 5 and not st["timed_out"], st
+            out[r] = torch.stack(gb).cpu().numpy().view(np.uint64)
+        except Exception as e:  # noqa: BLE001 -- reported by the main thread
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs, errs
+    for r in range(world):
+        assert out[r] is not None and (out[r][0] == want).all() and (out[r][1] == want).all()
+    for c in ctxs:
+        c.close()
