@@ -89,6 +89,9 @@ int phant_gpu_synchronize(phant_gpu_ctx* ctx);
  * once: message i = msgs[off[i] .. off[i+1]) (CSR byte offsets, any alignment, any length incl. 0);
  * out = n*32 digest bytes.  keccak256WithPrefix (hasher.zig:10-17) is the same call on prefix||data. */
 int phant_gpu_keccak256_batch(phant_gpu_ctx* ctx, const uint8_t* msgs, const uint64_t* off, uint64_t n, uint8_t* out);
+/* The same for DEVICE pointers when the caller knows total_bytes = off[n] - off[0]: nothing is read back, the call is
+ * asynchronous on the context's stream (the entry point above needs one host synchronisation to learn the total). */
+int phant_gpu_keccak256_batch_async(phant_gpu_ctx* ctx, const uint8_t* msgs, const uint64_t* off, uint64_t n, uint64_t total_bytes, uint8_t* out);
 
 /* M -- == mptize (src/mpt/mpt.zig:38-45).  Keys are byte strings sorted lexicographically (a strict
  * prefix first: KeyVal.lessThan, mpt.zig:31-33), CSR; values CSR.  n == 0 -> empty_mpt_root
@@ -229,7 +232,7 @@ int phant_gpu_comm_init_local(phant_gpu_ctx** ctxs, int n); /* one process: n co
                                                                drive each context from its own host thread */
 int phant_gpu_comm_info(const phant_gpu_ctx* ctx, int* rank, int* world, int* nccl_version);
 /* Optional PEER TRANSPORT for the gathered accept bitmap (same node, NVLink): a collective call that maps one small symmetric
- * region of every rank into every other rank (cudaIpc between processes, peer access inside one process).  Afterwards
+ * region of every rank into every other rank (cudaIpc; one process per GPU -- contexts that share a process keep NCCL).  Afterwards
  * device-pointer calls of phant_gpu_verify_proofs_sharded with equal, 64-aligned shards of at most max_n_global proofs need
  * no collective launch: the walk kernel's epilogue stores each ballot word straight into every rank's gathered bitmap and
  * publishes the step, and the comm stream only waits for the peers' words and copies the bitmap out.  Everything else keeps

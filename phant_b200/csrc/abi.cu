@@ -288,6 +288,18 @@ extern "C" int phant_gpu_keccak256_batch(phant_gpu_ctx* ctx, const uint8_t* msgs
     return PHANT_GPU_OK;
 }
 
+// device pointers with the total supplied by the caller: fully asynchronous on the context's stream (the plain entry point
+// has to read off[n] back, one host synchronisation per call)
+extern "C" int phant_gpu_keccak256_batch_async(phant_gpu_ctx* ctx, const uint8_t* msgs, const uint64_t* off, uint64_t n, uint64_t total_bytes,
+                                               uint8_t* out)
+{
+    if (!ctx || (n && (!off || !out)) || (total_bytes && !msgs)) return PHANT_GPU_E_INVALID;
+    if (!(ctx->flags & PHANT_GPU_FLAG_DEVICE_PTRS)) return PHANT_GPU_E_INVALID;
+    if (n == 0) return PHANT_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    return ctx->hash_csr(msgs, off, n, total_bytes, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // V: proof verification
 // ------------------------------------------------------------------------------------------------

@@ -359,14 +359,9 @@ extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_glo
     p->region[rank] = mine;
     for (int r = 0; ok && r < world; ++r) {
         if (r == rank) continue;
-        if (all[r].pid == (uint64_t)getpid()) { // one process, several contexts: plain peer access
-            int can = 0;
-            cudaDeviceCanAccessPeer(&can, ctx->device, all[r].dev);
-            if (!can) { ok = 0; break; }
-            const cudaError_t e = cudaDeviceEnablePeerAccess(all[r].dev, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
-            cudaGetLastError();
-            p->region[r] = (uint8_t*)(uintptr_t)all[r].ptr;
+        if (all[r].pid == (uint64_t)getpid()) { // several contexts of ONE process: not supported by this transport (NCCL stays)
+            ok = 0;
+            break;
         } else {
             void* q = nullptr;
             if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }

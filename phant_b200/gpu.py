@@ -55,7 +55,7 @@ class TrieDesc(C.Structure):
 EXPORTS = [
     "phant_gpu_abi_version", "phant_gpu_create", "phant_gpu_destroy", "phant_gpu_set_flags", "phant_gpu_set_stream", "phant_gpu_strerror",
     "phant_gpu_last_error", "phant_gpu_get_stats", "phant_gpu_reset_stats", "phant_gpu_synchronize",
-    "phant_gpu_keccak256_batch", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_ecrecover_batch", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
+    "phant_gpu_keccak256_batch", "phant_gpu_keccak256_batch_async", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_ecrecover_batch", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
     "phant_gpu_comm_get_unique_id", "phant_gpu_comm_init", "phant_gpu_comm_init_local", "phant_gpu_comm_info", "phant_gpu_comm_enable_peer", "phant_gpu_comm_peer_status", "phant_gpu_comm_fence",
@@ -90,6 +90,7 @@ def _lib():
     L.phant_gpu_reset_stats.argtypes = [vp]
     L.phant_gpu_synchronize.argtypes = [vp]
     L.phant_gpu_keccak256_batch.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    L.phant_gpu_keccak256_batch_async.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp]
     L.phant_gpu_mpt_root.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_mpt_roots.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, vp]
     L.phant_gpu_state_root.argtypes = [vp, C.POINTER(Accounts), vp]
@@ -184,6 +185,10 @@ class Context:
     # K
     def keccak256_batch(self, msgs, off, n, out):
         self._chk(_lib().phant_gpu_keccak256_batch(self._h, _ptr(msgs), _ptr(off), n, _ptr(out)), "keccak256_batch")
+
+    def keccak256_batch_async(self, msgs, off, n, total_bytes, out):
+        """device pointers, total supplied: no read-back, asynchronous on the context's stream"""
+        self._chk(_lib().phant_gpu_keccak256_batch_async(self._h, _ptr(msgs), _ptr(off), n, total_bytes, _ptr(out)), "keccak256_batch_async")
 
     # M
     def mpt_root(self, keys, key_off, vals, val_off, n):

@@ -161,54 +161,3 @@ def _check_two_process_gather(tmp_path, oracle, n, world, peer):
                 got = np.concatenate([bits[q * per: q * per + (gpu.shard_range(n, q, world)[1] - gpu.shard_range(n, q, world)[0])] for q in range(world)])
                 assert (got == want).all(), (r, name)
 
-
-@pytest.mark.gpu
-def test_one_process_two_contexts_peer_transport(oracle):
-    """one process, one context + one host thread per GPU (phant_gpu_comm_init_local): the peer transport inside a process is
-    plain peer access (no cudaIpc); five overlapping device-pointer steps per thread, both threads must end with the whole
-    accept bitmap"""
-    if _n_gpus() < 2:
-        pytest.skip("needs two GPUs (gpurun --gpus 2)")
-    import threading
-    import torch
-    from phant_b200 import gpu
-    n, world = 64 * 1024, 2
-    ctxs = [gpu.Context(r, gpu.FLAG_DEVICE_PTRS) for r in range(world)]
-    gpu.comm_init_local(ctxs)
-    o = oracle.synth_c2(n, depth=8, threads=4)
-    want = oracle.verify_proofs(*o, threads=4)[0]
-    out, errs = [None] * world, []
-
-    def run(r):
-        try:
-            torch.cuda.set_device(r)
-            ctx = ctxs[r]
-            ctx.comm_enable_peer(n)
-            lo, hi = gpu.shard_range(n, r, world)
-            w = oracle.synth_c2(hi - lo, depth=8, first=lo, threads=2)
-            d = [torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(f"cuda:{r}") for a in w]
-            d_nodes = torch.zeros(d[0].numel() + 64, dtype=torch.uint8, device=f"cuda:{r}")
-            d_nodes[:d[0].numel()] = d[0]
-            gb = [torch.zeros(gpu.sharded_bitmap_words(n, world), dtype=torch.int64, device=f"cuda:{r}") for _ in range(2)]
-            d_status = torch.zeros(hi - lo, dtype=torch.uint8, device=f"cuda:{r}")
-            torch.cuda.synchronize(r)
-            for k in range(5):
-                ctx.verify_proofs_sharded(hi - lo, n, d_nodes, d[1], d[2], d[3], d[4], hi - lo, gb[k & 1], d_status)
-            ctx.comm_fence()
-            ctx.synchronize()
-            st = ctx.comm_peer_status()
-            assert st["enabled"] and st["steps"] == 5 and not st["timed_out"], st
-            out[r] = torch.stack(gb).cpu().numpy().view(np.uint64)
-        except Exception as e:  # noqa: BLE001 -- reported by the main thread
-            errs.append((r, repr(e)))
-
-    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join(timeout=120)
-    assert not errs, errs
-    for r in range(world):
-        assert out[r] is not None and (out[r][0] == want).all() and (out[r][1] == want).all()
-    for c in ctxs:
-        c.close()

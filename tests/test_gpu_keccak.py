@@ -140,5 +140,9 @@ def test_regrouping_by_block_count_is_a_permutation(oracle):
         ctx.keccak256_batch(d_data, d_off, n, d_out)
         ctx.synchronize()
         assert (d_out.cpu().numpy() == want).all()
-    assert ctx.stats()["keccak_perms"] == 2 * int((lens // 136 + 1).sum())
+    d_out = torch.full((n, 32), 0xEE, dtype=torch.uint8, device="cuda")
+    ctx.keccak256_batch_async(d_data, d_off, n, int(off[-1]), d_out)   # total supplied: no read-back inside the call
+    ctx.synchronize()
+    assert (d_out.cpu().numpy() == want).all()
+    assert ctx.stats()["keccak_perms"] == 3 * int((lens // 136 + 1).sum())
     ctx.close()

@@ -119,6 +119,12 @@ pub const Gpu = struct {
         if (c.phant_gpu_comm_init(self.ctx, id, rank, world) != 0) return error.GpuBackend;
     }
 
+    /// Optional, collective: map every rank's bitmap region into every other rank (NVLink); equal-shard device-pointer calls of
+    /// verifyProofsSharded then gather inside the walk kernel.  error.GpuBackend = not possible here, NCCL stays in use.
+    pub fn commEnablePeer(self: *Gpu, max_proofs: u64) Error!void {
+        if (c.phant_gpu_comm_enable_peer(self.ctx, max_proofs) != 0) return error.GpuBackend;
+    }
+
     /// verifyProofs for this rank's shard of a batch of n_global proofs (phant_gpu_shard_range); on return global_bitmap
     /// (phant_gpu_sharded_bitmap_words(n_global, world) words) holds every rank's accept bits.
     pub fn verifyProofsSharded(self: *Gpu, local: *const c.phant_gpu_proof_batch, n_global: u64, global_bitmap: []u64, status: ?[]u8) Error!void {
