@@ -421,7 +421,10 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
     CU(cudaMemsetAsync(ctx->d_bitmap.ptr, 0, bm_bytes, s));
     CU(cudaMemcpyAsync(ctx->d_roots.ptr, in->roots32, 32 * in->n_roots, cudaMemcpyHostToDevice, s));
     ctx->stats.h2d_bytes += total + 8 * (n_nodes + 1) + 8 * (np + 1) + 32 * np + 32 * in->n_roots;
-    const uint64_t target_bytes = 48ull << 20; // per chunk: large enough for PCIe efficiency, small enough to start early
+    // per chunk: large enough for PCIe efficiency, small enough to start early (PHANT_GPU_CHUNK_MB: development knob)
+    static uint64_t chunk_mb = 0;
+    if (!chunk_mb) { const char* e = getenv("PHANT_GPU_CHUNK_MB"); const long v = e ? atol(e) : 0; chunk_mb = v >= 1 && v <= 4096 ? (uint64_t)v : 48; }
+    const uint64_t target_bytes = chunk_mb << 20;
     uint64_t p0 = 0;
     size_t chunk = 0;
     // the copy stream must not overwrite buffers a previous call's kernels may still read

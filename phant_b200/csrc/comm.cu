@@ -7,9 +7,10 @@
 //   NCCL    ncclAllGather of every rank's words, issued on the context's own COMM STREAM behind an event, so the next
 //           batch's Keccak launch never waits for a peer; the walk that next writes the same destination buffer waits for
 //           exactly that collective (callers that alternate two buffers never wait in steady state).
-//   peer    (PHANT_GPU_COMM_PEER, same node) the walk kernel's epilogue stores each ballot word straight into every
-//           rank's bitmap through NVLink peer mappings (cudaIpc / cudaDeviceEnablePeerAccess), followed by one flag store
-//           per peer; there is no collective launch at all -- phant_gpu_comm_fence() waits on the flags.
+//   peer    (phant_gpu_comm_enable_peer; same node, one process per GPU) the walk kernel's epilogue stores each ballot word
+//           straight into every rank's bitmap through NVLink peer mappings (cudaIpc), followed by one flag store per peer
+//           from the last CTA; there is no collective launch at all -- a small kernel on the comm stream waits on the flags
+//           and copies the gathered bitmap out.
 //
 // NCCL is dlopen'ed (libnccl.so.2): a single-GPU user of libphantgpu.so has no NCCL dependency, and inside a torch process
 // the already loaded copy is reused.  Every failure maps to PHANT_GPU_E_COMM with the NCCL text in phant_gpu_last_error.

@@ -1672,11 +1672,16 @@ __global__ void st_scatter_roots_kernel(const uint8_t* __restrict__ roots, const
         present[b] = cnt[u] ? 1 : 0;
     }
 }
-__global__ void st_parent_flag_kernel(const uint32_t* __restrict__ child, uint32_t cnt, uint32_t* __restrict__ parent, uint32_t* __restrict__ first)
+// the number of valid children stays on the device (*cnt_ptr <= bound): no host read-back per dense level
+__global__ void st_parent_flag_kernel(const uint32_t* __restrict__ child, const uint32_t* __restrict__ cnt_ptr, uint32_t bound, uint32_t* __restrict__ parent,
+                                      uint32_t* __restrict__ first)
 {
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
-        parent[j] = child[j] >> 4;
-        first[j] = j == 0 || (child[j - 1] >> 4) != (child[j] >> 4);
+    const uint32_t cnt = *cnt_ptr < bound ? *cnt_ptr : bound;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j <= bound; j += gridDim.x * blockDim.x) {
+        if (j < cnt) {
+            parent[j] = child[j] >> 4;
+            first[j] = j == 0 || (child[j - 1] >> 4) != (child[j] >> 4);
+        } else first[j] = 0;
     }
 }
 // One dense-top node per thread: rlp([ref or "" x 16, ""]) over the children that exist (src/mpt/mpt.zig:218-247), built in the
@@ -1684,10 +1689,12 @@ __global__ void st_parent_flag_kernel(const uint32_t* __restrict__ child, uint32
 // an extension / its child (mpt.zig:83-106): that breaks the dense-top premise and is reported through *violation.
 __global__ void __launch_bounds__(FR_WARPS * 32)
 st_top_branch_kernel(const uint8_t* __restrict__ child_level, const uint8_t* __restrict__ child_present, const uint32_t* __restrict__ parents /*nullable*/,
-                     uint32_t count, uint8_t* __restrict__ level, uint8_t* __restrict__ present, uint32_t* __restrict__ violation)
+                     uint32_t count, const uint32_t* __restrict__ count_ptr /*nullable: the count lives on the device, `count` is its bound*/,
+                     uint8_t* __restrict__ level, uint8_t* __restrict__ present, uint32_t* __restrict__ violation)
 {
     extern __shared__ __align__(16) uint8_t fr_smem[];
     const uint32_t slot = (uint32_t)__cvta_generic_to_shared(fr_smem) + threadIdx.x * FR_SLOT;
+    if (count_ptr && *count_ptr < count) count = *count_ptr;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t p = parents ? parents[i] : i;
         uint32_t mask = 0;
@@ -1813,28 +1820,29 @@ int st_rebuild(phant_gpu_trie* t, const uint32_t* d_list, uint32_t nb, bool all)
     uint32_t* viol = (uint32_t*)ctx->d_b3.ptr + 12;
     CU(cudaMemsetAsync(viol, 0, 4, s));
     const uint32_t* child = d_list;
-    uint32_t ccount = nb;
+    uint32_t cbound = nb;                       // upper bound of the children count; the exact count stays on the device
+    uint32_t* cnt_dev = (uint32_t*)ctx->d_b3.ptr + 13;
+    CU(cudaMemcpyAsync(cnt_dev, &nb, 4, cudaMemcpyHostToDevice, s));
     const unsigned fr_cap = (unsigned)keccak_num_sms(dev) * 3;
     for (int d = (int)L - 1; d >= 0; --d) {
         const uint32_t* plist = nullptr;
-        uint32_t pcount = 1u << (4 * d);
+        uint32_t pbound = 1u << (4 * d);
+        const uint32_t* pcount_dev = nullptr;
         if (!all) { // distinct parents of the (sorted) dirty children
             uint32_t* uniq = ping[d & 1];
-            st_parent_flag_kernel<<<grid1d(dev, ccount, 256), 256, 0, s>>>(child, ccount, par, flag);
-            CU(cudaMemsetAsync(flag + ccount, 0, 4, s));
-            RC(st_scan_u32(ctx, flag, pos, ccount + 1));
-            st_compact_kernel<<<grid1d(dev, ccount, 256), 256, 0, s>>>(par, flag, pos, ccount, uniq);
-            uint32_t pc = 0;
-            CU(cudaMemcpyAsync(&pc, pos + ccount, 4, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            pcount = pc;
+            st_parent_flag_kernel<<<grid1d(dev, cbound + 1, 256), 256, 0, s>>>(child, cnt_dev, cbound, par, flag);
+            RC(st_scan_u32(ctx, flag, pos, cbound + 1));
+            st_compact_kernel<<<grid1d(dev, cbound, 256), 256, 0, s>>>(par, flag, pos, cbound, uniq);
+            CU(cudaMemcpyAsync(cnt_dev, pos + cbound, 4, cudaMemcpyDeviceToDevice, s)); // the parents are the next level's children
+            if (cbound < pbound) pbound = cbound;
             plist = uniq;
             child = uniq;
-            ccount = pc;
+            cbound = pbound;
+            pcount_dev = cnt_dev;
             ctx->stats.launches += 3;
         }
-        const unsigned g = (pcount + FR_WARPS * 32 - 1) / (FR_WARPS * 32);
-        st_top_branch_kernel<<<g < fr_cap ? g : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(top + 32 * level_base(d + 1), pres + level_base(d + 1), plist, pcount,
+        const unsigned g = (pbound + FR_WARPS * 32 - 1) / (FR_WARPS * 32);
+        st_top_branch_kernel<<<g < fr_cap ? g : fr_cap, FR_WARPS * 32, FR_SMEM, s>>>(top + 32 * level_base(d + 1), pres + level_base(d + 1), plist, pbound, pcount_dev,
                                                                                top + 32 * level_base(d), pres + level_base(d), viol);
         ctx->stats.launches++;
     }
