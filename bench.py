@@ -42,6 +42,7 @@ PROOFS_PER_GPU = 1_000_000
 DEPTH = 8
 ALGO_BYTES_PER_PROOF = 3900  # 7*532 + 112 node bytes + 32 key + 32 root
 PERMS_PER_PROOF = 29
+DEFAULT_TRANSPORT = "nccl"  # "peer": the walk kernel's fused gather over NVLink mappings (validated at N=2; N=8 pending)
 METRIC = "mpt_proofs_verified_per_sec"
 UNIT = "proofs/s"
 
@@ -494,7 +495,8 @@ def run_gpu(args, rank, world, local_rank):
     transport = "none (1 GPU)"
     if world > 1:
         transport = "nccl"
-        if os.environ.get("PHANT_BENCH_TRANSPORT", "peer") == "peer":
+        # default = what has been confirmed on an 8-GPU box in this round; PHANT_BENCH_TRANSPORT overrides
+        if os.environ.get("PHANT_BENCH_TRANSPORT", DEFAULT_TRANSPORT) == "peer":
             try:  # collective: every rank takes the same branch (the library agrees on the outcome with one all-reduce)
                 ctx.comm_enable_peer(world * PROOFS_PER_GPU)
                 transport = "peer"
