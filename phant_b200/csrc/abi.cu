@@ -423,7 +423,7 @@ extern "C" int phant_gpu_verify_proofs(phant_gpu_ctx* ctx, const phant_gpu_proof
     ctx->stats.h2d_bytes += total + 8 * (n_nodes + 1) + 8 * (np + 1) + 32 * np + 32 * in->n_roots;
     // per chunk: large enough for PCIe efficiency, small enough to start early (PHANT_GPU_CHUNK_MB: development knob)
     static uint64_t chunk_mb = 0;
-    if (!chunk_mb) { const char* e = getenv("PHANT_GPU_CHUNK_MB"); const long v = e ? atol(e) : 0; chunk_mb = v >= 1 && v <= 4096 ? (uint64_t)v : 48; }
+    if (!chunk_mb) { const char* e = getenv("PHANT_GPU_CHUNK_MB"); const long v = e ? atol(e) : 0; chunk_mb = v >= 1 && v <= 4096 ? (uint64_t)v : 128; }
     const uint64_t target_bytes = chunk_mb << 20;
     uint64_t p0 = 0;
     size_t chunk = 0;
