@@ -17,6 +17,7 @@
 #include "ctx.cuh"
 #include "keccak_f1600.cuh"
 
+#include <chrono>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
@@ -39,6 +40,29 @@ using namespace phant;
     } while (0)
 
 namespace {
+
+// development knob PHANT_GPU_TRACE=1: wall time of the phases of a sparse-trie update on stderr (adds a synchronisation per phase)
+struct PhaseTrace {
+    cudaStream_t s;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTrace(cudaStream_t st) : s(st)
+    {
+        static int env = -1;
+        if (env < 0) { const char* e = getenv("PHANT_GPU_TRACE"); env = e && *e == '1'; }
+        on = env == 1;
+        if (on) { cudaStreamSynchronize(s); t0 = std::chrono::steady_clock::now(); }
+    }
+    void mark(const char* what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[phant trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 
 constexpr uint32_t NONE = 0xffffffffu;
 constexpr uint32_t KIND_LEAF = 1u << 30, KIND_NODE = 2u << 30, KIND_MASK = 3u << 30, IDX_MASK = ~KIND_MASK;
@@ -515,6 +539,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
     phant_gpu_ctx* ctx = this;
     cudaStream_t s = stream;
     if (n_seg == 0) return PHANT_GPU_OK;
+    PhaseTrace trf(s);
     const Keys k{d_keys, d_key_off};
     const Vals vals{d_vals, d_val_off};
     const uint32_t cap = n ? n : 1;
@@ -606,6 +631,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         stats.launches += 3;
     }
 
+    trf.mark("    forest: check + BFS");
     // ---- leaves: sizes -> offsets -> encode -> hash -> references (only the leaves the cache cannot answer) ----
     uint8_t* leaf_digests = nullptr;
     if (n) {
@@ -658,6 +684,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
         }
     }
 
+    trf.mark("    forest: leaves");
     // ---- units, deepest level first: branch, then the extension above it where there is one ----
     for (int L = (int)level_beg.size() - 1; L >= 0; --L) {
         const uint32_t lb = level_beg[L], lc = level_cnt[L], le = level_ext[L];
@@ -702,6 +729,7 @@ int phant_gpu_ctx::build_forest(const uint8_t* d_keys, const uint32_t* d_key_off
             stats.launches++;
         }
     }
+    trf.mark("    forest: units bottom-up");
     gather_roots_kernel<<<grid1d(device, n_seg, 128), 128, 0, s>>>(t, n_seg, leaf_digests, d_roots);
     stats.launches++;
     CU(cudaGetLastError());
@@ -1760,6 +1788,7 @@ int st_rebuild(phant_gpu_trie* t, const uint32_t* d_list, uint32_t nb, bool all)
     uint8_t* top = (uint8_t*)sp->top.ptr;
     uint8_t* pres = (uint8_t*)sp->present.ptr;
     if (n == 0) { memcpy(sp->root, EMPTY_ROOT_H, 32); return PHANT_GPU_OK; }
+    PhaseTrace tr(s);
     // ranges and sizes of the buckets
     RC(sp->sa.reserve(ctx, 4ull * (nb + 2) * 3 + 64));
     uint32_t* lo = (uint32_t*)sp->sa.ptr;
@@ -1796,7 +1825,9 @@ int st_rebuild(phant_gpu_trie* t, const uint32_t* d_list, uint32_t nb, bool all)
         RC(sp->sd.reserve(ctx, vbytes + 64));
         st_gather_vals_kernel<<<grid1d(dev, mk, 256, 32), 256, 0, s>>>((const uint8_t*)sp->arena.ptr, grec, gvoff, mk, (uint8_t*)sp->sd.ptr);
         ctx->stats.launches += 3;
+        tr.mark("  bucket ranges + gathers");
         RC(ctx->build_forest(gkeys, gkoff, (const uint8_t*)sp->sd.ptr, gvoff, mk, seg_off, nb, seg_of_key, (uint8_t*)sp->sroots.ptr, -1, L, gcache, gcache_out));
+        tr.mark("  build_forest");
         st_scatter_cache_kernel<<<grid1d(dev, nb, 256, 32), 256, 0, s>>>(lo, seg_off, nb, gcache_out, cache_tab);
         ctx->stats.launches++;
     }
@@ -1847,6 +1878,7 @@ int st_rebuild(phant_gpu_trie* t, const uint32_t* d_list, uint32_t nb, bool all)
         ctx->stats.launches++;
     }
     CU(cudaGetLastError());
+    tr.mark("  dense levels");
     uint32_t v = 0;
     CU(cudaMemcpyAsync(sp->root, top, 32, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(&v, viol, 4, cudaMemcpyDeviceToHost, s));
@@ -1908,7 +1940,10 @@ int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, 
     if (vb) CU(cudaMemcpyAsync(dv, vals, vb, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(raw_voff, val_off, 4ull * (m + 1), cudaMemcpyHostToDevice, s));
     ctx->stats.h2d_bytes += 32ull * m + vb + 4ull * (m + 1);
+    PhaseTrace tr(s);
+    tr.mark("stage dirty (H2D)");
     RC(ctx->sort_by_segment_and_hash(raw_k, nullptr, m, perm, sp->ssort));
+    tr.mark("sort dirty keys");
     gather_rows32_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(raw_k, perm, m, dk);
     st_gather_voff_kernel<<<grid1d(dev, m, 256), 256, 0, s>>>(raw_voff, perm, m, dvoff, dlen);
     // ---- classify against the table ----
@@ -1932,6 +1967,7 @@ int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, 
     CU(cudaMemcpyAsync(&app_bytes, app_off + m, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     ctx->stats.launches += 5;
+    tr.mark("classify + scans + readback");
     if (hc[2]) return PHANT_GPU_E_INVALID; // the same key twice in one update
     const uint32_t n_ins = hc[0], n_del = hc[1];
     // ---- values into the arena (grown with contents preserved; compaction is a rebuild-time concern) ----
@@ -1948,6 +1984,7 @@ int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, 
                                                             (uint8_t*)sp->cache[sp->cur].ptr);
     sp->arena_used += app_bytes;
     ctx->stats.launches++;
+    tr.mark("append values");
     // ---- merge (skipped for pure value updates) ----
     const uint32_t new_n = n - n_del + n_ins;
     if (n_ins || n_del) {
@@ -1968,6 +2005,7 @@ int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, 
         sp->cur = nxt;
         sp->n = new_n;
     }
+    tr.mark("merge");
     sp->updates++;
     if (new_n == 0) {
         sp->L = 0;
@@ -1995,6 +2033,7 @@ int strie_update(phant_gpu_trie* t, const uint8_t* keys32, const uint8_t* vals, 
         rc = st_rebuild(t, list, nb, false);
         if (rc == 1) rc = st_set_L_and_rebuild_all(t, sp->L - 1); // a dense node lost all but one child: fewer dense levels
     }
+    tr.mark("rebuild (buckets + top)");
     if (rc) return rc;
     memcpy(out_root, sp->root, 32);
     ctx->stats.d2h_bytes += 36;
