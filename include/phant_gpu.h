@@ -239,6 +239,7 @@ int phant_gpu_comm_info(const phant_gpu_ctx* ctx, int* rank, int* world, int* nc
  * using NCCL.  PHANT_GPU_E_COMM when a mapping is not possible on some rank: nothing changes, NCCL stays in use.  A rank
  * that stops answering makes the waiting kernels give up after 4 s; phant_gpu_comm_peer_status reports it. */
 int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_global);
+int phant_gpu_comm_disable_peer(phant_gpu_ctx* ctx); /* collective: unmap, back to the NCCL gather */
 int phant_gpu_comm_peer_status(phant_gpu_ctx* ctx, int* enabled, uint64_t* steps, int* timed_out);
 int phant_gpu_comm_fence(phant_gpu_ctx* ctx);   /* the context's stream waits (on the device) for every collective issued so far */
 int phant_gpu_comm_destroy(phant_gpu_ctx* ctx); /* also done by phant_gpu_destroy */

@@ -250,6 +250,23 @@ extern "C" int phant_gpu_comm_init_local(phant_gpu_ctx** ctxs, int n)
     return PHANT_GPU_OK;
 }
 
+// collective: back to the NCCL gather (barrier first: nobody unmaps a region a peer's kernels could still be storing into)
+extern "C" int phant_gpu_comm_disable_peer(phant_gpu_ctx* ctx)
+{
+    if (!ctx) return PHANT_GPU_E_INVALID;
+    if (!ctx->peer) return PHANT_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) CU(cudaStreamSynchronize(ctx->comm_stream));
+    NcclApi* api = nccl_api();
+    if (api && ctx->comm && ctx->d_comm.ptr) {
+        NC(api->AllReduce(ctx->d_comm.ptr, ctx->d_comm.ptr, 1, ncclInt32, ncclMin, (ncclComm_t)ctx->comm, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    peer_release(ctx);
+    return PHANT_GPU_OK;
+}
+
 extern "C" int phant_gpu_comm_peer_status(phant_gpu_ctx* ctx, int* enabled, uint64_t* steps, int* timed_out)
 {
     if (!ctx) return PHANT_GPU_E_INVALID;

@@ -58,7 +58,7 @@ EXPORTS = [
     "phant_gpu_keccak256_batch", "phant_gpu_keccak256_batch_async", "phant_gpu_mpt_root", "phant_gpu_mpt_roots", "phant_gpu_state_root", "phant_gpu_state_subtree_roots", "phant_gpu_ecrecover_batch", "phant_gpu_verify_proofs", "phant_gpu_verify_witness",
     "phant_gpu_logs_bloom", "phant_gpu_trie_open", "phant_gpu_trie_root", "phant_gpu_trie_update", "phant_gpu_trie_close",
     "phant_gpu_synth_sizes", "phant_gpu_synth",
-    "phant_gpu_comm_get_unique_id", "phant_gpu_comm_init", "phant_gpu_comm_init_local", "phant_gpu_comm_info", "phant_gpu_comm_enable_peer", "phant_gpu_comm_peer_status", "phant_gpu_comm_fence",
+    "phant_gpu_comm_get_unique_id", "phant_gpu_comm_init", "phant_gpu_comm_init_local", "phant_gpu_comm_info", "phant_gpu_comm_enable_peer", "phant_gpu_comm_disable_peer", "phant_gpu_comm_peer_status", "phant_gpu_comm_fence",
     "phant_gpu_comm_destroy", "phant_gpu_shard_range", "phant_gpu_sharded_bitmap_words", "phant_gpu_verify_proofs_sharded",
     "phant_gpu_block_reject_counts", "phant_gpu_nibble_owner", "phant_gpu_state_root_sharded",
 ]
@@ -111,6 +111,7 @@ def _lib():
     L.phant_gpu_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
     L.phant_gpu_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.phant_gpu_comm_enable_peer.argtypes = [vp, C.c_uint64]
+    L.phant_gpu_comm_disable_peer.argtypes = [vp]
     L.phant_gpu_comm_peer_status.argtypes = [vp, C.POINTER(C.c_int), u64p, C.POINTER(C.c_int)]
     L.phant_gpu_comm_fence.argtypes = [vp]
     L.phant_gpu_comm_destroy.argtypes = [vp]
@@ -263,6 +264,10 @@ class Context:
         """collective; afterwards equal-shard device-pointer calls of verify_proofs_sharded gather through peer memory
         (the walk's epilogue) instead of a NCCL launch.  Raises PhantGpuError(-5) when a mapping is impossible: NCCL stays."""
         self._chk(_lib().phant_gpu_comm_enable_peer(self._h, max_n_global), "comm_enable_peer")
+
+    def comm_disable_peer(self):
+        """collective: unmap the peer regions, back to the NCCL gather"""
+        self._chk(_lib().phant_gpu_comm_disable_peer(self._h), "comm_disable_peer")
 
     def comm_peer_status(self):
         e, st, to = C.c_int(), C.c_uint64(), C.c_int()
