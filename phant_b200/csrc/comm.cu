@@ -146,6 +146,7 @@ struct phant_gpu_ctx::Peer {
     uint8_t* region[PEER_MAX_WORLD] = {}; // every rank's region as mapped here (region[rank] = my own allocation)
     bool ipc_opened[PEER_MAX_WORLD] = {};
     uint64_t step = 0;
+    bool usable = false;               // set once every rank has mapped every region (a half-built object is only ever released)
     static constexpr size_t HDR = 1024;
     unsigned long long* ready(int r, int b, int src) const { return (unsigned long long*)region[r] + (b * PEER_MAX_WORLD + src); }
     unsigned long long* done(int r, int b, int src) const { return (unsigned long long*)region[r] + (2 * PEER_MAX_WORLD + b * PEER_MAX_WORLD + src); }
@@ -270,11 +271,11 @@ extern "C" int phant_gpu_comm_disable_peer(phant_gpu_ctx* ctx)
 extern "C" int phant_gpu_comm_peer_status(phant_gpu_ctx* ctx, int* enabled, uint64_t* steps, int* timed_out)
 {
     if (!ctx) return PHANT_GPU_E_INVALID;
-    if (enabled) *enabled = ctx->peer ? 1 : 0;
-    if (steps) *steps = ctx->peer ? ctx->peer->step : 0;
+    if (enabled) *enabled = ctx->peer && ctx->peer->usable ? 1 : 0;
+    if (steps) *steps = ctx->peer && ctx->peer->usable ? ctx->peer->step : 0;
     if (timed_out) {
         *timed_out = 0;
-        if (ctx->peer) {
+        if (ctx->peer && ctx->peer->usable) {
             CU(cudaSetDevice(ctx->device));
             uint32_t e = 0;
             CU(cudaMemcpy(&e, ctx->peer->err(ctx->peer->rank), 4, cudaMemcpyDeviceToHost));
@@ -340,7 +341,8 @@ extern "C" int phant_gpu_comm_fence(phant_gpu_ctx* ctx)
 extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_global)
 {
     if (!ctx || max_n_global == 0) return PHANT_GPU_E_INVALID;
-    if (ctx->peer) return PHANT_GPU_OK;
+    if (ctx->peer && ctx->peer->usable) return PHANT_GPU_OK;
+    if (ctx->peer) peer_release(ctx); // left over from a failed attempt
     const int world = ctx->comm_world, rank = ctx->comm_rank;
     NcclApi* api = nccl_api();
     if (world < 2 || world > PEER_MAX_WORLD || !api || !ctx->comm) { snprintf(ctx->last_error, sizeof ctx->last_error, "peer transport needs a communicator of 2..16 ranks"); return PHANT_GPU_E_COMM; }
@@ -353,10 +355,13 @@ extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_glo
     const size_t bytes = phant_gpu_ctx::Peer::HDR + 2 * 8 * p->cap_words + 64;
     uint8_t* mine = nullptr;
     int ok_local = 1;
-    if (cudaMalloc((void**)&mine, bytes) != cudaSuccess) { cudaGetLastError(); ok_local = 0; }
+    if (cudaMalloc((void**)&mine, bytes) != cudaSuccess) { cudaGetLastError(); ok_local = 0; mine = nullptr; }
+    p->region[rank] = mine;
+    ctx->peer = p; // owned by the context from here on: every error return below leaves a non-usable object that
+                   // phant_gpu_comm_disable_peer / phant_gpu_comm_destroy release
     PeerRec* h = (PeerRec*)ctx->h_comm;
     static_assert(sizeof(PeerRec) == 88, "record layout");
-    if ((size_t)(world + 1) * sizeof(PeerRec) > 16384) { if (mine) cudaFree(mine); delete p; return PHANT_GPU_E_INVALID; }
+    if ((size_t)(world + 1) * sizeof(PeerRec) > 16384) { peer_release(ctx); return PHANT_GPU_E_INVALID; }
     memset(h, 0, sizeof(PeerRec));
     if (ok_local) {
         CU(cudaMemsetAsync(mine, 0, bytes, s));
@@ -364,7 +369,7 @@ extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_glo
         h->pid = (uint64_t)getpid(); h->ptr = (uint64_t)(uintptr_t)mine; h->dev = ctx->device;
     }
     h->pad = ok_local;
-    if (int rc = ctx->d_comm.reserve(ctx, sizeof(PeerRec) * (world + 1))) { if (mine) cudaFree(mine); delete p; return rc; }
+    if (int rc = ctx->d_comm.reserve(ctx, sizeof(PeerRec) * (world + 1))) { peer_release(ctx); return rc; }
     uint8_t* d = (uint8_t*)ctx->d_comm.ptr;
     CU(cudaMemcpyAsync(d + sizeof(PeerRec) * rank, h, sizeof(PeerRec), cudaMemcpyHostToDevice, s));
     NC(api->AllGather(d + sizeof(PeerRec) * rank, d, sizeof(PeerRec), ncclUint8, (ncclComm_t)ctx->comm, s));
@@ -374,7 +379,6 @@ extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_glo
     // every rank takes the same decision from the same records; mapping failures are exchanged in a second round
     int ok = 1;
     for (int r = 0; r < world; ++r) ok &= all[r].pad;
-    p->region[rank] = mine;
     for (int r = 0; ok && r < world; ++r) {
         if (r == rank) continue;
         if (all[r].pid == (uint64_t)getpid()) { // several contexts of ONE process: not supported by this transport (NCCL stays)
@@ -394,7 +398,6 @@ extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_glo
     NC(api->AllReduce(d, d, 1, ncclInt32, ncclMin, (ncclComm_t)ctx->comm, s));
     CU(cudaMemcpyAsync(flag, d, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    ctx->peer = p;
     if (!*flag) {
         peer_release(ctx);
         snprintf(ctx->last_error, sizeof ctx->last_error, "peer mapping (cudaIpc / peer access) not available on every rank");
@@ -425,7 +428,7 @@ extern "C" int phant_gpu_verify_proofs_sharded(phant_gpu_ctx* ctx, const phant_g
         const uint64_t my_words = (hi - lo + 63) / 64;
         phant_gpu_ctx::Peer* pr = ctx->peer;
         // (the choice must be the same on every rank: it depends on n_global and world only -- equal, 64-aligned shards)
-        if (world > 1 && pr && n_global && n_global % (64ull * world) == 0 && per_words * world <= pr->cap_words) {
+        if (world > 1 && pr && pr->usable && n_global && n_global % (64ull * world) == 0 && per_words * world <= pr->cap_words) {
             // ---- peer transport: the walk's epilogue stores into every rank's buffer and publishes the step; the comm stream
             // only waits for the other ranks' words, copies the gathered bitmap out and releases the buffer ----
             NvtxRange nvtx("phant:gather(peer)");
