@@ -394,10 +394,10 @@ def bench_c4_sparse(ctx, gpu, torch, dev, steps):
             "scaling": "replicas only"}
 
 
-def bench_c5(ctx, gpu, torch, dev, rank, world, steps, barrier):
-    """BASELINE configs[4]: 1000 blocks x 300 tx, deduplicated witness per block, BLOCKS sharded over the ranks; per-block
-    verdict = no rejected proof; one all-reduce over u32 reject_count[1000] (phant_gpu_block_reject_counts)."""
-    import numpy as np
+def build_c5(ctx, torch, dev, rank, world):
+    """this rank's share of the C5 witness, built on the device (setup, untimed).  Called BEFORE any communicator exists: once
+    NCCL has enabled peer access between the 8 GPUs every cudaMalloc of torch's allocator is mapped into every peer, and the
+    many small tensors of the builder made it take 20-60 s on an 8-GPU box (0.1-0.2 s on one or two GPUs)."""
     from phant_b200 import synth_blocks
     n_blocks = int(os.environ.get("PHANT_BENCH_C5_BLOCKS", "1000"))
     per = (n_blocks + world - 1) // world
@@ -405,7 +405,14 @@ def bench_c5(ctx, gpu, torch, dev, rank, world, steps, barrier):
     t0 = time.perf_counter()
     w = synth_blocks.synth_blocks(ctx, dev, b0, b1 - b0, txs=300)
     torch.cuda.synchronize()
-    gen_s = time.perf_counter() - t0
+    return w, n_blocks, time.perf_counter() - t0
+
+
+def bench_c5(ctx, gpu, torch, dev, rank, world, steps, barrier, built):
+    """BASELINE configs[4]: 1000 blocks x 300 tx, deduplicated witness per block, BLOCKS sharded over the ranks; per-block
+    verdict = no rejected proof; one all-reduce over u32 reject_count[1000] (phant_gpu_block_reject_counts)."""
+    import numpy as np
+    w, n_blocks, gen_s = built
     n = w["n_proofs"]
     ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
     status = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
@@ -482,9 +489,10 @@ def run_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # before any barrier: forking nvidia-smi must not sit between a barrier and a timed region
+    ctx = gpu.Context(local_rank)
+    c5_built = None if args.skip_extras else build_c5(ctx, torch, dev, rank, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ctx = gpu.Context(local_rank)
     if world > 1:
         # multi-GPU goes through the C ABI (comm.cu): the id travels over whatever channel the host has -- here torch.distributed
         idt = torch.zeros(gpu.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
@@ -627,7 +635,8 @@ def run_gpu(args, rank, world, local_rank):
         ex_steps = max(3, min(args.steps, 5))
         ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
         extras["c3"] = bench_c3(ctx, gpu, torch, dev, rank, world, ex_steps, barrier)
-        extras["c5"] = bench_c5(ctx, gpu, torch, dev, rank, world, ex_steps, barrier)
+        extras["c5"] = bench_c5(ctx, gpu, torch, dev, rank, world, ex_steps, barrier, c5_built)
+        c5_built = None
         barrier()
         if rank == 0:
             extras["keccak_by_size"] = bench_mhs(ctx, gpu, torch, dev)
