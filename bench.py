@@ -507,6 +507,7 @@ def run_gpu(args, rank, world, local_rank):
         if os.environ.get("PHANT_BENCH_TRANSPORT", DEFAULT_TRANSPORT) == "peer":
             try:  # collective: every rank takes the same branch (the library agrees on the outcome with one all-reduce)
                 ctx.comm_enable_peer(world * PROOFS_PER_GPU)
+                assert ctx.comm_peer_status()["enabled"]
                 transport = "peer"
             except gpu.PhantGpuError:
                 transport = "nccl (peer mapping unavailable)"
@@ -584,6 +585,7 @@ def run_gpu(args, rank, world, local_rank):
     dt_local, per_step, st, status_ok, bitmap_ok = measure()
     peer_status = ctx.comm_peer_status() if world > 1 else None
     if transport == "peer":
+        assert peer_status["steps"] == args.warmup + args.steps, peer_status  # every step really went over the peer transport
         # safety net: had the fused gather failed on ANY rank (a bounded wait gave up, or the gathered bits are wrong), every rank
         # drops to the NCCL gather and the measurement is repeated -- the line then says so
         bad = 0.0 if (status_ok and bitmap_ok and not peer_status["timed_out"]) else 1.0

@@ -403,6 +403,7 @@ extern "C" int phant_gpu_comm_enable_peer(phant_gpu_ctx* ctx, uint64_t max_n_glo
         snprintf(ctx->last_error, sizeof ctx->last_error, "peer mapping (cudaIpc / peer access) not available on every rank");
         return PHANT_GPU_E_COMM;
     }
+    p->usable = true;
     return PHANT_GPU_OK;
 }
 
