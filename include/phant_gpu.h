@@ -15,7 +15,10 @@
  *     hold witnesses in HBM).  Device-pointer inputs must be 16-byte aligned and the byte buffers
  *     (msgs / nodes) must be readable for 16 bytes past their last offset.  Host inputs are
  *     validated (monotone offsets, index ranges) before anything is launched; device-pointer inputs
- *     are TRUSTED to be well-formed CSR -- the node CONTENTS are never trusted in either mode;
+ *     are TRUSTED to be well-formed CSR -- the node CONTENTS are never trusted in either mode.  Device-pointer calls are
+ *     ASYNCHRONOUS on the context's stream (its own non-blocking stream unless phant_gpu_set_stream gave it the caller's):
+ *     ordering against the caller's own kernels that produce the inputs / consume the outputs is the caller's job --
+ *     share the stream, or synchronise on both sides;
  *   - a context owns one device, one stream and its scratch memory; it is not re-entrant: one
  *     context per host thread, or lock around it (phant calls runBlock from httpz worker threads,
  *     src/main.zig:143-149);

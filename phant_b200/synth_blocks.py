@@ -60,7 +60,13 @@ def _hash_rows(ctx, rows):
     flat[: n * L] = rows.reshape(-1)
     off = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
     out = torch.empty(n, 32, dtype=torch.uint8, device=dev)
+    # the library works on the CONTEXT's stream (a non-blocking one unless the caller set another): torch's kernels that
+    # filled `flat` / `off` must have finished before it reads them, and it must have finished before torch reads `out`
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
     ctx.keccak256_batch(flat, off, n, out)
+    if dev.type == "cuda":
+        ctx.synchronize()
     return out
 
 
