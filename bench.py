@@ -533,6 +533,7 @@ def run_gpu(args, rank, world, local_rank):
     # one side stream shared by the library's kernels and torch's ops (torch's default stream has handle 0, which
     # phant_gpu_set_stream reads as "restore the private stream"); the library's collectives run on its own comm stream
     side = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()  # the zero fills above ran on torch's default stream; from here everything shares `side`
     torch.cuda.set_stream(side)
     ctx.set_stream(side.cuda_stream)
 

@@ -51,6 +51,7 @@ def test_world_size_one_sharded_call_is_the_plain_call(oracle):
     d_nodes[:d[0].numel()] = d[0]
     d_bitmap = torch.zeros(len(bitmap), dtype=torch.int64, device="cuda")
     d_status = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # torch's stream and the context's stream are not ordered against each other
     ctx.verify_proofs_sharded(n, n, d_nodes, d[1], d[2], d[3], d[4], n, d_bitmap, d_status)
     ctx.comm_fence()
     ctx.synchronize()
@@ -107,6 +108,7 @@ def _worker(rank, world, n, tmp, peer=False):
     words = gpu.sharded_bitmap_words(n, world)
     gb = [torch.zeros(words, dtype=torch.int64, device="cuda") for _ in range(2)]
     d_status = torch.zeros(hi - lo, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # torch's stream and the context's stream are not ordered against each other
     for k in range(7 if peer else 5):  # alternate the two buffers; steps overlap on the comm stream
         ctx.verify_proofs_sharded(hi - lo, n, d_nodes, d[1], d[2], d[3], d[4], hi - lo, gb[k & 1], d_status)
     ctx.comm_fence()

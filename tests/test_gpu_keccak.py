@@ -92,6 +92,7 @@ def test_device_pointer_mode_and_size(ctx, oracle):
     data[size:2 * size] = data[0:size]                       # message 1 == message 0
     off = torch.arange(0, n + 1, dtype=torch.int64, device="cuda") * size
     out = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     for flags in (0, 1 << 4):
         out.zero_()
         ctx.set_flags(gpu.FLAG_DEVICE_PTRS | flags)
@@ -137,10 +138,12 @@ def test_regrouping_by_block_count_is_a_permutation(oracle):
     d_off = torch.from_numpy(off.view(np.int64)).cuda()
     for _ in range(2):
         d_out = torch.full((n, 32), 0xEE, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         ctx.keccak256_batch(d_data, d_off, n, d_out)
         ctx.synchronize()
         assert (d_out.cpu().numpy() == want).all()
     d_out = torch.full((n, 32), 0xEE, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     ctx.keccak256_batch_async(d_data, d_off, n, int(off[-1]), d_out)   # total supplied: no read-back inside the call
     ctx.synchronize()
     assert (d_out.cpu().numpy() == want).all()

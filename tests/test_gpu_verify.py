@@ -101,6 +101,7 @@ def test_device_synth_equals_oracle_synth(ctx, oracle, which):
     d_first = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
     d_keys = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
     d_roots = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # torch's fills run on torch's stream, the library on its own (non-blocking) one
     ctx.synth(which, n, d_nodes, d_off, d_first, d_keys, d_roots, depth=8, first=1000)
     o = oracle.synth_c2(n, depth=8, first=1000) if which == 2 else oracle.synth_c3(n, first=1000)
     assert n_bytes == int(o[1][-1]) and n_nodes == len(o[1]) - 1
@@ -130,6 +131,7 @@ def test_full_size_c2_property(ctx):
     ctx.synth(2, n, d_nodes, d_off, d_first, d_keys, d_roots, depth=8)
     d_status = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
     ctx.verify_proofs(n, d_nodes, d_off, d_first, d_keys, d_roots, n, d_bitmap, d_status, None, None)
     ctx.synchronize()
@@ -192,6 +194,7 @@ def test_deduplicated_block_witness(ctx, oracle):
     d = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v).cuda() for k, v in w.items() if isinstance(v, np.ndarray)}
     d_status = torch.zeros(n, dtype=torch.uint8, device="cuda")
     d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
     ctx.verify_proofs(n, d["nodes"], d["node_off"], d["proof_first"], d["keys32"], d["roots32"], n, d_bitmap, d_status, None, None,
                       n_nodes=w["n_nodes"], nodes_bytes=w["n_bytes"], node_index=d["node_index"])
@@ -221,6 +224,7 @@ def test_full_size_c3_property(ctx):
     ctx.synth(3, n, d_nodes, d_off, d_first, d_keys, d_roots)
     d_status = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
     ctx.verify_proofs(n, d_nodes, d_off, d_first, d_keys, d_roots, n, d_bitmap, d_status, None, None, n_nodes=n_nodes, nodes_bytes=n_bytes)
     ctx.synchronize()
@@ -422,6 +426,7 @@ def test_device_built_block_witnesses_vs_oracle(ctx, oracle):
     d_voff = torch.zeros(n, dtype=torch.int64, device="cuda")
     d_vlen = torch.zeros(n, dtype=torch.int32, device="cuda")
     d_counts = torch.zeros(first + nb, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
     ctx.set_flags(gpu.FLAG_DEVICE_PTRS)
     ctx.verify_proofs(n, w["nodes"], w["node_off"], w["proof_first"], w["keys32"], w["roots32"], n, d_bitmap, d_status, d_voff, d_vlen,
                       n_nodes=w["n_nodes"], nodes_bytes=w["n_bytes"], node_index=w["node_index"])
