@@ -106,6 +106,28 @@ int main()
         }
         expect(H(state::StateDB::rootFromSubtreeRoots(g, all)), big_root, ("sharded StateDB.root world " + std::to_string(world)).c_str());
     }
+    // ---- StateDB.root() block after block on a resident trie: load `big`, then apply only what a "block" touched ----
+    {
+        state::ResidentStateTrie rt(g);
+        expect(H(rt.root()), H(mpt::empty_mpt_root), "ResidentStateTrie empty");
+        std::map<Address, const state::AccountState*> all;
+        for (const auto& [a, acc] : big.db) all[a] = &acc;
+        expect(H(rt.apply(all)), big_root, "ResidentStateTrie: load == StateDB.root()");
+        // a block: two balances change, one storage slot is written, one account is created, one destroyed
+        std::map<Address, const state::AccountState*> touched;
+        auto it = big.db.begin();
+        it->second.balance[31] ^= 0x55; touched[it->first] = &it->second; ++it;
+        it->second.nonce += 7; touched[it->first] = &it->second; ++it;
+        { std::array<uint8_t, 32> k{}, v{}; k[0] = 9; v[31] = 3; it->second.storage[k] = v; touched[it->first] = &it->second; ++it; }
+        const Address gone = it->first;
+        touched[gone] = nullptr;
+        Address fresh{}; fresh[3] = 0xee; fresh[19] = 0x42;
+        big.db[fresh].balance[30] = 1;
+        touched[fresh] = &big.db[fresh];
+        const Hash32 after = rt.apply(touched);
+        big.db.erase(gone);
+        expect(H(after), H(big.root(g)), "ResidentStateTrie: after a block == StateDB.root() of the new state");
+    }
     // ---- sender recovery: the geth-generated vector of src/crypto/ecdsa.zig:38-48, and a signature that recovers nothing ----
     {
         const Bytes hm = X("05e0e0ff09b01e5626daac3165b82afa42be29197b82e8a5a8800740ee7519d2");

@@ -273,6 +273,90 @@ private:
         }
     };
 };
+
+// StateDB.root() block after block (hook src/blockchain/blockchain.zig:83-85) without rebuilding the state trie: the account
+// trie lives on the device (U kind 1, a sparse resident secure trie); after a block the host hands over ONLY the accounts
+// the block touched.  Storage roots of touched accounts are plain mptize calls (their tries are small); the account leaf is
+// rlp([nonce, balance, storage_root, keccak(code)]) as in evmone/test/state/mpt_hash.cpp:15-36.
+class ResidentStateTrie {
+public:
+    explicit ResidentStateTrie(Gpu& g) : g_(g)
+    {
+        phant_gpu_trie_desc d{};
+        d.kind = 1;
+        g_.check(phant_gpu_trie_open(g_.ctx(), &d, &t_), "ResidentStateTrie open");
+    }
+    ~ResidentStateTrie() { phant_gpu_trie_close(t_); }
+    ResidentStateTrie(const ResidentStateTrie&) = delete;
+    ResidentStateTrie& operator=(const ResidentStateTrie&) = delete;
+
+    Hash32 root()
+    {
+        Hash32 r;
+        g_.check(phant_gpu_trie_root(t_, r.data()), "ResidentStateTrie root");
+        return r;
+    }
+    // `touched`: address -> new account state, or nullptr for a destroyed account.  Returns the new state root.
+    Hash32 apply(const std::map<Address, const AccountState*>& touched)
+    {
+        if (touched.empty()) return root();
+        std::vector<Bytes> addrs, codes;
+        for (const auto& [a, acc] : touched) {
+            addrs.emplace_back(a.begin(), a.end());
+            codes.push_back(acc ? acc->code : Bytes{});
+        }
+        const std::vector<Hash32> keys = hasher::keccak256_batch(g_, addrs), code_hashes = hasher::keccak256_batch(g_, codes);
+        Bytes k32, vals;
+        std::vector<uint32_t> voff{0};
+        size_t i = 0;
+        for (const auto& [a, acc] : touched) {
+            k32.insert(k32.end(), keys[i].begin(), keys[i].end());
+            if (acc) {
+                std::vector<mpt::KeyVal> slots;  // secure storage trie: keccak(slot) -> rlp(trimmed value), zero values dropped
+                std::vector<Bytes> slot_keys;
+                for (const auto& [sk, sv] : acc->storage) slot_keys.emplace_back(sk.begin(), sk.end());
+                const std::vector<Hash32> hk = slot_keys.empty() ? std::vector<Hash32>{} : hasher::keccak256_batch(g_, slot_keys);
+                std::vector<std::pair<Hash32, Bytes>> kv;
+                size_t j = 0;
+                for (const auto& [sk, sv] : acc->storage) {
+                    size_t z = 0;
+                    while (z < 32 && sv[z] == 0) ++z;
+                    if (z < 32) kv.emplace_back(hk[j], rlp_str(Bytes(sv.begin() + z, sv.end())));
+                    ++j;
+                }
+                std::sort(kv.begin(), kv.end());
+                for (const auto& e : kv) slots.push_back(mpt::KeyVal::init(Bytes(e.first.begin(), e.first.end()), e.second));
+                const Hash32 sroot = mpt::mptize(g_, slots);
+                Bytes body = rlp::encode_uint(acc->nonce);
+                size_t z = 0;
+                while (z < 32 && acc->balance[z] == 0) ++z;
+                const Bytes bal = rlp_str(Bytes(acc->balance.begin() + z, acc->balance.end()));
+                body.insert(body.end(), bal.begin(), bal.end());
+                body.push_back(0xa0); body.insert(body.end(), sroot.begin(), sroot.end());
+                body.push_back(0xa0); body.insert(body.end(), code_hashes[i].begin(), code_hashes[i].end());
+                const Bytes leaf = rlp::wrap_list(body);
+                vals.insert(vals.end(), leaf.begin(), leaf.end());
+            } // destroyed account: empty value = delete
+            voff.push_back((uint32_t)vals.size());
+            ++i;
+        }
+        Hash32 r;
+        g_.check(phant_gpu_trie_update(t_, k32.data(), vals.data(), voff.data(), touched.size(), r.data()), "ResidentStateTrie apply");
+        return r;
+    }
+
+private:
+    static Bytes rlp_str(const Bytes& b) // short strings only (<= 55 bytes): what account fields need
+    {
+        if (b.empty()) return {0x80};
+        if (b.size() == 1 && b[0] < 0x80) return b;
+        Bytes out{(uint8_t)(0x80 + b.size())};
+        out.insert(out.end(), b.begin(), b.end());
+        return out;
+    }
+    Gpu& g_;
+    phant_gpu_trie* t_ = nullptr;
+};
 } // namespace state
 
 namespace signer {
